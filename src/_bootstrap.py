@@ -1,0 +1,8 @@
+"""Put the repository root on sys.path so ``python src/<entrypoint>.py`` works
+from a checkout, exactly like the reference's flat ``src/`` scripts."""
+import os
+import sys
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
