@@ -1,0 +1,392 @@
+// The gradient-aggregation hot path as ONE kernel:  arrival -> commit mask -> reduce over
+// NVLink peer memory -> x 1/count -> SGD -> replicate weights -> bf16 shadow.
+//
+// Replaces, per training step, the reference's parameter-server round trip (SURVEY §2.5
+// X1-X8; src/sync_replicas_optimizer_modified/sync_replicas_optimizer_modified.py:330-398):
+//   X1 apply_grad (worker->PS reduce with staleness filter)  -> arrival bit + peer loads
+//   X2 take_grad(K|N|1) (mean over accepted gradients)       -> commit mask, sum, x 1/popcount
+//   X3 apply_gradients + global_step++ on the PS             -> SGD in the same loop, epoch word
+//   X4 weight pulls by every worker                          -> owner pushes its shard to all peers
+//   X5/X6 token enqueue / dequeue barrier                    -> done flags
+// No NCCL call and no separate scale / optimizer kernel runs on this path.
+//
+// Every rank launches this kernel on its own GPU.  All buffers live in symmetric memory
+// (same layout on every rank, peers mapped through CUDA IPC / VMM), so a kernel addresses a
+// peer's gradient arena, parameter arena and control block directly.
+//
+// Two arrival policies:
+//   FULL  (K == N):  all-to-all arrival flags, one NVLink hop.
+//   KOFN  (K <  N):  arrival bitmap + commit word owned by the chief (rank 0): a rank ORs its
+//                    bit into the chief's bitmap; whoever first observes popcount >= K publishes
+//                    the frozen bitmap with a CAS and broadcasts it to every rank's control
+//                    block.  Ranks in the mask form the reduce team: team member i of c owns
+//                    shard i of c, sums the *masked* contributors, divides by c and pushes the
+//                    new weights to ALL N ranks.  A rank that is not in the mask ("late") or
+//                    arrives for an already committed step ("stale", reference …modified.py:59-62)
+//                    has its gradient discarded, waits until the pushes have landed, fast-forwards
+//                    to the newest global step and continues: replicas never diverge and nobody
+//                    waits for a straggler.
+#include <stddef.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "host_utils.h"
+
+namespace dm {
+
+constexpr int SYNC_MAX_RANKS = 8;
+constexpr int SYNC_RING = 64;          // commit-word ring (steps)
+constexpr int SYNC_THREADS = 512;
+constexpr int TIMING_RING = 1024;      // per-rank arrival-timestamp ring (steps)
+
+// Control block, one per rank, in symmetric memory.  Words written remotely are spread over
+// separate 128-byte lines.
+struct SyncCtrl {
+  // ---- written by peers -----------------------------------------------------------------
+  volatile uint32_t arrive[SYNC_MAX_RANKS * 32];     // [p*32]: peer p arrived for epoch (value = epoch+1)
+  volatile uint32_t done[SYNC_MAX_RANKS * 32];       // [p*32]: peer p's pushes for step s landed (value = s+1)
+  volatile unsigned long long commit_local[SYNC_RING];  // ((step+1) << 32) | mask, broadcast by the committer
+  // ---- authoritative on the chief only ------------------------------------------------------
+  unsigned int bitmap[SYNC_RING];                    // arrival bitmap of step s at [s % RING]
+  unsigned long long commit[SYNC_RING];              // ((step+1) << 32) | mask
+  volatile uint32_t global_step;                     // number of committed steps
+  volatile uint32_t last_in_mask[SYNC_MAX_RANKS];    // (last step in whose mask rank q was) + 1
+  uint32_t pad0[32];
+  // ---- local ----------------------------------------------------------------------------------
+  uint32_t epoch;                // global step of my weights (device-resident so CUDA graphs replay)
+  uint32_t cta_counter;          // grid-wide completion counter
+  volatile uint32_t decided_tag; // epoch+1 once `decided_mask` is valid for this launch
+  volatile uint32_t decided_mask;
+  volatile uint32_t decided_late;   // 1: my gradient is not part of the mean
+  volatile uint32_t decided_target; // epoch to move to after this launch
+  uint32_t error;                // watchdog: 1 = arrival timeout, 2 = done timeout
+  uint32_t accepted_steps, dropped_steps;
+  uint32_t last_mask, last_count, last_late;
+  uint32_t pad1[32];
+  unsigned long long t_arrive[TIMING_RING];   // %globaltimer at arrival, per local step (cdf telemetry)
+  unsigned long long t_start[TIMING_RING];    // %globaltimer stamped by the step's first kernel
+};
+
+struct SyncPeers {
+  SyncCtrl* ctrl[SYNC_MAX_RANKS];
+  float* params[SYNC_MAX_RANKS];
+  const float* grads[SYNC_MAX_RANKS];
+};
+
+struct SyncArgs {
+  int rank, nranks, k;
+  int numel4;                 // arena length in float4
+  float lr0, decay_rate;      // staircase exponential decay evaluated on device (reference K12)
+  int decay_steps;
+  float drop_keep;            // gradient drop-connect keep probability, <= 0: off (reference K14)
+  uint32_t drop_seed;
+  unsigned long long timeout_ns;
+  __nv_bfloat16* shadow;      // local bf16 copy of the parameter arena (tensor-core operand source)
+};
+
+// ---- system-scope memory helpers ----------------------------------------------------------------
+DMNIST_DEVICE uint32_t ld_acquire_sys(const volatile uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+DMNIST_DEVICE unsigned long long ld_acquire_sys64(const volatile unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+DMNIST_DEVICE void st_release_sys(volatile uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+DMNIST_DEVICE void st_release_sys64(volatile unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+DMNIST_DEVICE float4 ld_peer_f4(const float* p) {   // peer data: read once, keep out of L1
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+DMNIST_DEVICE void st_peer_f4(float* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+DMNIST_DEVICE float device_lr(const SyncArgs& a, uint32_t step) {
+  const float p = (float)(step / (uint32_t)max(a.decay_steps, 1));
+  return a.lr0 * __powf(a.decay_rate, p);
+}
+
+// Poll until pred() or the watchdog fires.
+template <class Pred>
+DMNIST_DEVICE bool spin_until(Pred pred, unsigned long long timeout_ns) {
+  if (pred()) return true;
+  const unsigned long long t0 = globaltimer_ns();
+  unsigned ns = 32;
+  while (!pred()) {
+    __nanosleep(ns);
+    if (ns < 256) ns *= 2;
+    if (globaltimer_ns() - t0 > timeout_ns) return false;
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Arrival + commit decision (executed by CTA 0, warp 0).  Publishes decided_* in the local ctrl.
+// ---------------------------------------------------------------------------------------------------
+template <bool KOFN>
+DMNIST_DEVICE void decide(const SyncPeers& P, const SyncArgs& a, SyncCtrl* me, uint32_t epoch) {
+  const int lane = threadIdx.x;
+  const uint32_t full_mask = (a.nranks >= 32) ? 0xffffffffu : ((1u << a.nranks) - 1u);
+  uint32_t mask = full_mask, late = 0, target = epoch + 1;
+  if (lane == 0) me->t_arrive[epoch % TIMING_RING] = globaltimer_ns();
+  __threadfence_system();   // my gradient arena (written by the backward kernels) is visible system-wide
+  if (!KOFN) {
+    if (lane < a.nranks) st_release_sys(&P.ctrl[lane]->arrive[a.rank * 32], epoch + 1);
+    bool ok = true;
+    if (lane < a.nranks)
+      ok = spin_until([&] { return ld_acquire_sys(&me->arrive[lane * 32]) >= epoch + 1; }, a.timeout_ns);
+    if (!__all_sync(0xffffffffu, ok) && lane == 0) me->error = 1;
+  } else {
+    SyncCtrl* chief = P.ctrl[0];
+    const int slot = epoch % SYNC_RING;
+    if (lane == 0) {
+      const unsigned long long want_tag = (unsigned long long)(epoch + 1);
+      // Commit words are broadcast into every rank's control block, so "is my step already
+      // committed?" is a local read (no NVLink round trip on the common path).
+      unsigned long long cw = ld_acquire_sys64(&me->commit_local[slot]);
+      if ((cw >> 32) < want_tag) {
+        // Not committed as far as I can see: OR my bit into the chief's bitmap.  Bitmap slots carry
+        // no tag: the committer of step s clears the slot of step s + RING/2, so a bit that lands
+        // after its step committed (the race below) is wiped half a lap before the slot is reused.
+        const unsigned int now = (atomicOr_system(&chief->bitmap[slot], 1u << a.rank) | (1u << a.rank)) & full_mask;
+        if (__popc(now) >= a.k) {
+          unsigned long long old = ld_acquire_sys64((volatile unsigned long long*)&chief->commit[slot]);
+          if ((old >> 32) < want_tag) {
+            const unsigned long long mine = (want_tag << 32) | (unsigned long long)now;
+            // exactly one winner publishes the frozen bitmap as the step's commit mask
+            if (atomicCAS_system(&chief->commit[slot], old, mine) == old) {
+              for (int q = 0; q < a.nranks; ++q)
+                if ((now >> q) & 1u) chief->last_in_mask[q] = epoch + 1;
+              __threadfence_system();
+              atomicMax_system((unsigned int*)&chief->global_step, epoch + 1);
+              for (int q = 0; q < a.nranks; ++q) st_release_sys64(&P.ctrl[q]->commit_local[slot], mine);
+              atomicExch_system(&chief->bitmap[(slot + SYNC_RING / 2) % SYNC_RING], 0u);
+            }
+          }
+        }
+        // wait for the commit word of my step to reach my control block
+        const bool ok = spin_until(
+            [&] { cw = ld_acquire_sys64(&me->commit_local[slot]); return (cw >> 32) >= want_tag; }, a.timeout_ns);
+        if (!ok) me->error = 1;
+      }
+      if ((cw >> 32) == want_tag) {
+        mask = (uint32_t)cw;
+        late = ((mask >> a.rank) & 1u) ? 0u : 1u;
+      } else {
+        mask = 0;   // committed at least one ring lap ago: stale beyond the ring
+        late = 1;
+      }
+      if (late) {
+        // stale / late (reference: push dropped, worker proceeds with the newest step): fast-forward
+        const uint32_t g = ld_acquire_sys(&chief->global_step);
+        target = g > epoch + 1 ? g : epoch + 1;
+      }
+    }
+    mask = __shfl_sync(0xffffffffu, mask, 0);
+    late = __shfl_sync(0xffffffffu, late, 0);
+    target = __shfl_sync(0xffffffffu, target, 0);
+  }
+  if (lane == 0) {
+    me->decided_mask = mask;
+    me->decided_late = late;
+    me->decided_target = target;
+    __threadfence();
+    st_release_sys(&me->decided_tag, epoch + 1);
+  }
+}
+
+template <bool KOFN>
+__global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_sgd_kernel(SyncPeers P, SyncArgs a) {
+  SyncCtrl* me = P.ctrl[a.rank];
+  __shared__ uint32_t s_mask, s_late, s_target, s_last;
+  const uint32_t epoch = me->epoch;   // stable for the whole launch (only the last CTA writes it, at exit)
+
+  if (blockIdx.x == 0 && threadIdx.x < 32) decide<KOFN>(P, a, me, epoch);
+  if (threadIdx.x == 0) {
+    spin_until([&] { return ld_acquire_sys(&me->decided_tag) == epoch + 1; }, a.timeout_ns * 2);
+    s_mask = me->decided_mask;
+    s_late = me->decided_late;
+    s_target = me->decided_target;
+  }
+  __syncthreads();
+  const uint32_t mask = s_mask, late = s_late;
+  const int count = __popc(mask);
+
+  if (!late && count > 0) {
+    // ---- reduce my shard over the contributors, SGD, push to every rank -------------------------
+    const int my_idx = __popc(mask & ((1u << a.rank) - 1u));
+    const int shard = (a.numel4 + count - 1) / count;
+    const int begin = my_idx * shard;
+    const int end = min(begin + shard, a.numel4);
+    const float scale = device_lr(a, epoch) / (float)count;
+    const uint32_t drop_thresh = a.drop_keep > 0.f ? (uint32_t)(a.drop_keep * 16777216.f) : 0u;
+    int contrib[SYNC_MAX_RANKS];
+    int nc = 0;
+    for (int q = 0; q < a.nranks; ++q)
+      if ((mask >> q) & 1u) contrib[nc++] = q;
+    const float* wsrc = P.params[a.rank];
+    for (int i = begin + blockIdx.x * SYNC_THREADS + threadIdx.x; i < end; i += gridDim.x * SYNC_THREADS) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+      for (int c = 0; c < nc; ++c) {
+        const int q = contrib[c];
+        float4 g = ld_peer_f4(P.grads[q] + 4 * (size_t)i);
+        if (drop_thresh) {   // drop-connect: contributor q's Bernoulli mask, no 1/p rescale (reference :414-416)
+          const uint32_t sm = a.drop_seed + epoch * 0x9E3779B9u + (uint32_t)q * 0x85EBCA77u;
+          g.x = dropout_keep(sm, 4u * i + 0, drop_thresh) ? g.x : 0.f;
+          g.y = dropout_keep(sm, 4u * i + 1, drop_thresh) ? g.y : 0.f;
+          g.z = dropout_keep(sm, 4u * i + 2, drop_thresh) ? g.z : 0.f;
+          g.w = dropout_keep(sm, 4u * i + 3, drop_thresh) ? g.w : 0.f;
+        }
+        acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+      }
+      float4 w = *reinterpret_cast<const float4*>(wsrc + 4 * (size_t)i);
+      w.x -= scale * acc.x; w.y -= scale * acc.y; w.z -= scale * acc.z; w.w -= scale * acc.w;
+      for (int q = 0; q < a.nranks; ++q) st_peer_f4(P.params[q] + 4 * (size_t)i, w);
+    }
+  }
+
+  // ---- grid-wide: all my pushes are out -> tell every rank ------------------------------------------
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last = (atomicAdd(&me->cta_counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last && !late && threadIdx.x < a.nranks) {
+    __threadfence_system();
+    st_release_sys(&P.ctrl[threadIdx.x]->done[a.rank * 32], epoch + 1);
+  }
+
+  // ---- wait until every team member's shard has landed in MY arena ---------------------------------
+  if (threadIdx.x < a.nranks) {
+    const int q = threadIdx.x;
+    uint32_t need = ((mask >> q) & 1u) ? epoch + 1 : 0u;
+    if (KOFN && late) need = ld_acquire_sys(&P.ctrl[0]->last_in_mask[q]);   // fast-forward: everything committed so far
+    const bool ok = spin_until([&] { return ld_acquire_sys(&me->done[q * 32]) >= need; }, a.timeout_ns);
+    if (!ok) me->error = 2;
+  }
+  __syncthreads();
+
+  // ---- local bf16 shadow of the fresh weights (operand source for the tcgen05 kernels) --------------
+  if (a.shadow != nullptr) {
+    const float* w = P.params[a.rank];
+    for (int i = blockIdx.x * SYNC_THREADS + threadIdx.x; i < a.numel4; i += gridDim.x * SYNC_THREADS) {
+      const float4 v = __ldcv(reinterpret_cast<const float4*>(w) + i);   // bypass L1: peers just wrote it
+      uint2 o;
+      o.x = pack_bf16x2(v.x, v.y);
+      o.y = pack_bf16x2(v.z, v.w);
+      *reinterpret_cast<uint2*>(a.shadow + 4 * (size_t)i) = o;
+    }
+  }
+
+  // ---- bookkeeping by the last CTA ---------------------------------------------------------------------
+  if (s_last && threadIdx.x == 0) {
+    me->last_mask = mask;
+    me->last_count = count;
+    me->last_late = late;
+    if (late) me->dropped_steps += 1; else me->accepted_steps += 1;
+    me->cta_counter = 0;
+    me->epoch = s_target;
+  }
+}
+
+// fp32 -> bf16 shadow refresh (after init / checkpoint restore, outside the hot loop).
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int n4) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    reinterpret_cast<uint2*>(dst)[i] = o;
+  }
+}
+
+// Device-side straggler injection: with probability `prob` (hash of the step) spin for `usec`.
+__global__ void straggler_delay_kernel(const SyncCtrl* ctrl, float prob, unsigned int usec, uint32_t seed) {
+  const uint32_t step = ctrl->epoch;
+  if (dropout_keep(seed, step, (uint32_t)(prob * 16777216.f))) {
+    const unsigned long long t0 = globaltimer_ns();
+    while (globaltimer_ns() - t0 < (unsigned long long)usec * 1000ull) __nanosleep(1000);
+  }
+}
+
+// Stamp the start of a step's compute (%globaltimer) for the cdf-mode telemetry.
+__global__ void stamp_start_kernel(SyncCtrl* ctrl) { ctrl->t_start[ctrl->epoch % TIMING_RING] = globaltimer_ns(); }
+
+}  // namespace dm
+
+extern "C" {
+
+int dm_sync_ctrl_bytes() { return (int)sizeof(dm::SyncCtrl); }
+
+// Offsets of host-readable fields (the Python side reads the control block through a view).
+int dm_sync_ctrl_offset(const char* field) {
+  using dm::SyncCtrl;
+#define DM_OFF(name) if (strcmp(field, #name) == 0) return (int)offsetof(SyncCtrl, name)
+  DM_OFF(epoch); DM_OFF(error); DM_OFF(accepted_steps); DM_OFF(dropped_steps); DM_OFF(last_mask);
+  DM_OFF(last_count); DM_OFF(last_late); DM_OFF(global_step); DM_OFF(t_arrive); DM_OFF(t_start);
+  DM_OFF(cta_counter);
+#undef DM_OFF
+  return -1;
+}
+
+// peers: arrays of `nranks` device pointers (index = rank; own entries are the local buffers).
+int dm_fused_sync_sgd(void* const* ctrl, void* const* params, void* const* grads, int rank, int nranks, int k,
+                      long long numel, float lr0, float decay_rate, int decay_steps, float drop_keep,
+                      unsigned int drop_seed, double timeout_ms, void* shadow_bf16, int ctas, void* stream_) {
+  using namespace dm;
+  if (nranks < 1 || nranks > SYNC_MAX_RANKS || (numel & 3) || k < 1 || k > nranks) return -1;
+  SyncPeers P;
+  for (int i = 0; i < SYNC_MAX_RANKS; ++i) {
+    const int j = i < nranks ? i : rank;
+    P.ctrl[i] = reinterpret_cast<SyncCtrl*>(ctrl[j]);
+    P.params[i] = reinterpret_cast<float*>(params[j]);
+    P.grads[i] = reinterpret_cast<const float*>(grads[j]);
+  }
+  SyncArgs a;
+  a.rank = rank; a.nranks = nranks; a.k = k; a.numel4 = (int)(numel / 4);
+  a.lr0 = lr0; a.decay_rate = decay_rate; a.decay_steps = decay_steps;
+  a.drop_keep = drop_keep; a.drop_seed = drop_seed;
+  a.timeout_ns = (unsigned long long)(timeout_ms * 1e6);
+  a.shadow = reinterpret_cast<__nv_bfloat16*>(shadow_bf16);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (ctas < 1) ctas = 32;
+  if (k < nranks) fused_sync_sgd_kernel<true><<<ctas, SYNC_THREADS, 0, stream>>>(P, a);
+  else            fused_sync_sgd_kernel<false><<<ctas, SYNC_THREADS, 0, stream>>>(P, a);
+  return (int)cudaGetLastError();
+}
+
+int dm_f32_to_bf16(const void* src, void* dst, long long numel, void* stream_) {
+  if (numel & 3) return -1;
+  dm::f32_to_bf16_kernel<<<148, 512, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      reinterpret_cast<const float*>(src), reinterpret_cast<__nv_bfloat16*>(dst), (int)(numel / 4));
+  return (int)cudaGetLastError();
+}
+
+int dm_straggler_delay(const void* ctrl, float prob, unsigned int usec, unsigned int seed, void* stream_) {
+  dm::straggler_delay_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      reinterpret_cast<const dm::SyncCtrl*>(ctrl), prob, usec, seed);
+  return (int)cudaGetLastError();
+}
+
+int dm_stamp_start(void* ctrl, void* stream_) {
+  dm::stamp_start_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(reinterpret_cast<dm::SyncCtrl*>(ctrl));
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,257 @@
+// tcgen05 GEMM for sm_100a:  D[M,N] (+)= A[M,K] * B[K,N],  bf16 in, fp32 accumulate in TMEM.
+//
+// Covers every dense GEMM of the models (reference ops K6/K8: tf.matmul, src/mnist.py:136,145,
+// and their gradients) without a single transpose kernel: each operand may be K-major or
+// MN-major in memory, so the TF layouts ([in,out] weights, [batch,features] activations) are
+// consumed as they are:
+//     fc fwd    D[b,out]  = X[b,in]   (A K-major)  * W[in,out]  (B MN-major)
+//     fc dgrad  D[b,in]   = dY[b,out] (A K-major)  * W[in,out]  (B K-major:  rows=in, K=out contiguous)
+//     fc wgrad  D[in,out] = X[b,in]   (A MN-major) * dY[b,out]  (B MN-major),  K = batch
+//
+// Structure (one 128 x BN output tile per CTA, optional split-K over gridDim.z):
+//     warp 0      TMA producer      cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx
+//     warp 1      MMA issuer        one elected lane issues tcgen05.mma; tcgen05.commit frees the stage
+//     warps 2-5   epilogue          tcgen05.ld (32 lanes x 32 columns) -> registers -> global
+#include "common.cuh"
+#include "host_utils.h"
+
+namespace dm {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_THREADS = 192;
+
+enum GemmEpilogue : int { EPI_STORE_F32 = 0, EPI_ATOMIC_F32 = 1, EPI_STORE_BF16 = 2 };
+
+struct GemmParams {
+  int M, N;        // logical output extent (predication)
+  int num_kb;      // ceil(K / 64)
+  int ldo;         // output leading dimension (elements)
+  void* out;
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = GEMM_STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + alignment slack
+};
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+  using S = GemmSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle atoms repeat every 1024 B: align the ring so descriptors need no base offset.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + GEMM_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + GEMM_STAGES;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * GEMM_BM;
+  const int n0 = blockIdx.y * BN;
+  // split-K: this CTA owns k-blocks [kb_begin, kb_end)
+  const int kb_begin = (int)(((long long)p.num_kb * blockIdx.z) / gridDim.z);
+  const int kb_end = (int)(((long long)p.num_kb * (blockIdx.z + 1)) / gridDim.z);
+  const int nkb = kb_end - kb_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < GEMM_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_holder);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % GEMM_STAGES;
+        const uint32_t ph = (i / GEMM_STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sA = smem + s * S::STAGE_BYTES;
+        uint8_t* sB = sA + S::A_BYTES;
+        mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+        const int k0 = (kb_begin + i) * GEMM_BK;
+        if (!A_MN) {
+          tma_load_2d(sA, &tmA, &full_bar[s], k0, m0);                 // box {64 k, 128 m}
+        } else {
+          tma_load_2d(sA, &tmA, &full_bar[s], m0, k0);                 // box {64 m, 64 k}
+          tma_load_2d(sA + 8192, &tmA, &full_bar[s], m0 + 64, k0);
+        }
+        if (!B_MN) {
+          tma_load_2d(sB, &tmB, &full_bar[s], k0, n0);                 // box {64 k, BN n}
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + j * 8192, &tmB, &full_bar[s], n0 + 64 * j, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, A_MN, B_MN);
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % GEMM_STAGES;
+      const uint32_t ph = (i / GEMM_STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after_sync();
+      if (elect_one()) {
+        const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + S::A_BYTES;
+        // K-major:  128 B rows (64 bf16 of K), 8-row groups 1024 B apart; K advances 32 B per UMMA_K.
+        // MN-major: 128 B k-rows (64 bf16 of M/N), 8-k groups 1024 B apart, 64-wide M/N chunks 8192 B
+        //           apart; K advances 16 k-rows = 2048 B per UMMA_K.
+        const uint64_t da0 = A_MN ? make_smem_desc(a_addr, 8192, 1024, SWZ_128B)
+                                  : make_smem_desc(a_addr, 16, 1024, SWZ_128B);
+        const uint64_t db0 = B_MN ? make_smem_desc(b_addr, 8192, 1024, SWZ_128B)
+                                  : make_smem_desc(b_addr, 16, 1024, SWZ_128B);
+#pragma unroll
+        for (int k = 0; k < GEMM_BK / 16; ++k) {
+          const uint64_t da = desc_advance(da0, (A_MN ? 2048u : 32u) * k);
+          const uint64_t db = desc_advance(db0, (B_MN ? 2048u : 32u) * k);
+          umma_bf16(tmem_base, da, db, idesc, (i | k) != 0);
+        }
+        umma_commit(&empty_bar[s]);                  // stage reusable once these MMAs retire
+        if (i == nkb - 1) umma_commit(tmem_full_bar);  // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------ epilogue -----------------------------------
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int row = m0 + q * 32 + lane;
+    if (nkb > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after_sync();
+    }
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      if (nkb > 0) {
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0;
+      }
+      const int col0 = n0 + c * 32;
+      if (row < p.M) {
+        if (EPI == EPI_STORE_F32) {
+          float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
+          if (col0 + 32 <= p.N && (p.ldo & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                               __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) o[j] = __uint_as_float(v[j]);
+          }
+        } else if (EPI == EPI_ATOMIC_F32) {
+          float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) atomicAdd(o + j, __uint_as_float(v[j]));
+        } else {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + col0;
+          if (col0 + 32 <= p.N && (p.ldo & 7) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 w;
+              w.x = pack_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+              w.y = pack_bf16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              w.z = pack_bf16x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+              w.w = pack_bf16x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+              *reinterpret_cast<uint4*>(o + j) = w;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) o[j] = __float2bfloat16(__uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<BN>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int splits,
+                       cudaStream_t stream) {
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, EPI>;
+  constexpr int smem = GemmSmem<BN>::TOTAL;
+  static bool configured = false;
+  if (!configured) {
+    DM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid((p.M + GEMM_BM - 1) / GEMM_BM, (p.N + BN - 1) / BN, splits);
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, p);
+  return (int)cudaGetLastError();
+}
+
+template <int BN, int EPI>
+static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+                          int splits, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch_gemm<BN, false, false, EPI>(tmA, tmB, p, splits, stream);
+  if (!a_mn && b_mn) return launch_gemm<BN, false, true, EPI>(tmA, tmB, p, splits, stream);
+  if (a_mn && !b_mn) return launch_gemm<BN, true, false, EPI>(tmA, tmB, p, splits, stream);
+  return launch_gemm<BN, true, true, EPI>(tmA, tmB, p, splits, stream);
+}
+
+}  // namespace dm
+
+// D[M,N] = A * B with bf16 operands.
+//   a_mn == 0: A is [M rows][K cols] (lda elements between rows);   a_mn == 1: A is [K rows][M cols].
+//   b_mn == 0: B is [N rows][K cols] (ldb);                          b_mn == 1: B is [K rows][N cols].
+//   epi: 0 store fp32, 1 atomicAdd fp32 (split-K; caller zeroes), 2 store bf16.   bn: 64 or 128.
+extern "C" int dm_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, int lda, int ldb, int ldo,
+                            int a_mn, int b_mn, int epi, int splits, int bn, void* stream_) {
+  using namespace dm;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if ((bn != 64 && bn != 128) || epi < 0 || epi > 2 || splits < 1) return -1;
+  if (splits > 1 && epi != EPI_ATOMIC_F32) return -2;
+  if ((lda & 7) || (ldb & 7)) return -3;   // TMA: global strides are multiples of 16 bytes
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!a_mn) rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, 128, 128);
+  else       rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, 64, 128);
+  if (rc) return 100 + rc;
+  if (!b_mn) rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, (uint32_t)bn, 128);
+  else       rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, 64, 128);
+  if (rc) return 200 + rc;
+  GemmParams p{M, N, (K + GEMM_BK - 1) / GEMM_BK, ldo, out};
+  if (splits > p.num_kb) splits = p.num_kb > 0 ? p.num_kb : 1;
+#define DM_DISPATCH(BN_, EPI_) return dispatch_major<BN_, EPI_>(a_mn != 0, b_mn != 0, tmA, tmB, p, splits, stream)
+  if (bn == 64) {
+    if (epi == 0) DM_DISPATCH(64, 0);
+    if (epi == 1) DM_DISPATCH(64, 1);
+    DM_DISPATCH(64, 2);
+  } else {
+    if (epi == 0) DM_DISPATCH(128, 0);
+    if (epi == 1) DM_DISPATCH(128, 1);
+    DM_DISPATCH(128, 2);
+  }
+#undef DM_DISPATCH
+}
