@@ -1,0 +1,257 @@
+#!/usr/bin/env python
+"""Headline benchmark: MNIST images/sec of the synchronous-replica LeNet training step.
+
+Metric / config (BASELINE.json): whole-box images/sec, device-timed, max over ranks;
+LeNet-like convnet (reference src/mnist.py:76-147, 1,663,370 parameters), bf16 tensor-core
+operands / fp32 accumulate + fp32 master weights, batch 256 per replica, plain SGD, K = N
+sync replicas, synthetic 28x28 data, random-init weights.  Weak scaling (per-GPU batch fixed).
+
+    python bench.py --gpus N --steps K --warmup W          # our engine (N>1: under torchrun, or self-spawned)
+    python bench.py --impl reference ...                   # the unmodified reference (unavailable here: TF1/py2)
+    python bench.py --impl torch_ddp ...                   # baseline/: torch + cuDNN/cuBLAS + NCCL (for BASELINE.md)
+
+One JSON line on stdout from rank 0.  Two measurements per run:
+  * ``value``  -- K steps replayed from the CUDA graph with inputs already on the device, rotating through a
+                  device-resident input pool larger than L2 (so every step reads cold inputs); CUDA events;
+  * ``e2e``    -- K steps through the public API (``engine.load_batch`` from pinned host memory ->
+                  ``engine.train_step`` -> device->host read of the loss) -- H2D and D2H inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "MNIST images/sec (whole box, device-timed, max over ranks)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_ddp"])
+    ap.add_argument("--batch", type=int, default=256, help="per-replica batch (BASELINE.json: 256)")
+    ap.add_argument("--k", type=int, default=-1, help="replicas_to_aggregate (-1 = all)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--straggler", default="", help="rank:prob:usec device-side delay injection")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks / throttle reasons sampled DURING the timed region
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = [(0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
+               (0x4, "sw_power_cap"), (0x80, "hw_power_brake_slowdown"), (0x2, "applications_clocks_setting")]
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        self.index, self.period = index, period_s
+        self.sm, self.reasons, self.sm_max = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self.sm.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS:
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_reference(args):
+    # The reference is Python-2 / TensorFlow<=1.0 / Twisted code with no setup.py; `pip install --no-index
+    # --target baseline/_ref /root/reference` fails ("Neither 'setup.py' nor 'pyproject.toml' found") and
+    # neither tensorflow nor twisted exists offline (DESIGN.md "Reference arm").
+    print(json.dumps({"impl": "reference",
+                      "unavailable": "reference is py2/TF<=1.0/Twisted with no setup.py; pip --no-index install fails "
+                                     "and tensorflow/twisted are absent offline"}))
+    return 0
+
+
+def maybe_self_spawn(args) -> bool:
+    """`python bench.py --gpus N` without torchrun: spawn the N ranks ourselves."""
+    if args.gpus > 1 and "RANK" not in os.environ:
+        from distributedmnist_b200.parallel.launcher import run_replicas
+        codes = run_replicas([os.path.abspath(__file__)] + sys.argv[1:], args.gpus)
+        sys.exit(max(codes))
+    return False
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    maybe_self_spawn(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from distributedmnist_b200.flags import FLAGS
+    from distributedmnist_b200.parallel.context import init_context, shutdown_context
+
+    if args.impl == "torch_ddp":
+        from baseline.torch_ddp import run_baseline
+        return run_baseline(args)
+
+    from distributedmnist_b200.engine_cuda import CudaLeNetEngine
+    from distributedmnist_b200.parallel.aggregators import SyncReplicasOptimizer, parse_straggler_spec
+    from distributedmnist_b200.parallel.fused import FusedBackend
+    from distributedmnist_b200.schedule import LearningRateSchedule, decay_steps_for
+
+    ctx = init_context(FLAGS, want_gpu=True)
+    if not ctx.on_gpu:
+        print(json.dumps({"metric": METRIC, "value": None, "error": "no CUDA device"}))
+        return 1
+    n, rank, B = ctx.world_size, ctx.rank, args.batch
+    k = n if args.k < 0 else args.k
+    backend = FusedBackend(ctx)
+    engine = CudaLeNetEngine(B, backend, seed=66478, rank=rank, use_graph=not args.no_graph)
+    sched = LearningRateSchedule(0.01, decay_steps_for(60000, B, 2.0, k), 0.999)
+    opt = SyncReplicasOptimizer(backend, sched, replicas_to_aggregate=k, total_num_replicas=n,
+                                straggler=parse_straggler_spec(args.straggler))
+    engine.attach_optimizer(opt)
+
+    # ---- synthetic data ------------------------------------------------------------------------------------
+    # host pool (pinned) for the e2e path; device pool > L2 (126 MB) for the device-timed path
+    g = torch.Generator().manual_seed(1234 + rank)
+    pool_n = 208                                             # 208 x 256 x 784 x 4 B = 167 MB > 126 MB L2
+    if B * 784 * 4 * pool_n < 160e6:
+        pool_n = int(160e6 / (B * 784 * 4)) + 1
+    h_imgs = (torch.rand(32, B, 28, 28, generator=g) - 0.5).pin_memory()
+    h_lbls = torch.randint(0, 10, (32, B), generator=g).pin_memory()
+    d_imgs = (torch.rand(pool_n, B, 28, 28, device=ctx.device) - 0.5)
+    d_lbls = torch.randint(0, 10, (pool_n, B), device=ctx.device)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if n > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step(i: int):
+        # inputs come from the device pool (cold in L2); slot buffers are what the captured graph reads
+        s = i & 1
+        engine.images[s].copy_(d_imgs[i % pool_n])
+        engine.labels[s].copy_(d_lbls[i % pool_n])
+        engine._slot = s
+        engine._copy_done[s].record()
+        engine.train_step()
+
+    def e2e_step(i: int):
+        engine.load_batch(h_imgs[i % 32], h_lbls[i % 32])     # pinned host -> device (copy stream)
+        engine.train_step()
+        return engine.read_loss_async()                       # device -> host, read one step later
+
+    # ---- warm-up (captures the graphs) ------------------------------------------------------------------------
+    for i in range(max(args.warmup, 3)):
+        device_step(i)
+    barrier()
+
+    # ---- device-timed K steps ------------------------------------------------------------------------------------
+    sampler = ClockSampler(ctx.device.index or 0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        device_step(i)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=ctx.device)
+    if n > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    launches = engine.launches_per_step * args.steps
+
+    # ---- end-to-end K steps (public API: pinned H2D every step, loss D2H every step) --------------------------------
+    for i in range(3):
+        e2e_step(i)[0].synchronize()
+    barrier()
+    e0.record()
+    pending = None
+    last_loss = 0.0
+    for i in range(args.steps):
+        ev = e2e_step(i)
+        if pending is not None:
+            pending[0].synchronize()
+            last_loss = float(pending[1][0])                  # the step's result is consumed on the host
+        pending = ev
+    pending[0].synchronize()
+    last_loss = float(pending[1][0])
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=ctx.device)
+    if n > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ms2_total = float(ms2.item())
+    backend.check_error()
+    info = engine.step_info()
+
+    if rank == 0:
+        value = n * B * args.steps / (ms_total / 1e3)
+        e2e_value = n * B * args.steps / (ms2_total / 1e3)
+        out = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": n, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "impl": "ours",
+            "config": {"model": "LeNet-like MNIST convnet (1,663,370 params, reference src/mnist.py)",
+                       "global_batch": n * B, "batch_per_replica": B, "seq_len": None,
+                       "parallelism": "dp%d (sync replicas, K=%d of %d, fused NVLink allreduce+SGD kernel)" % (n, k, n),
+                       "optimizer": "SGD, staircase exp-decay LR evaluated on device",
+                       "l2": "inputs rotate through a %d MB device pool (> 126 MB L2)" % int(d_imgs.numel() * 4 / 1e6),
+                       "cuda_graph": not args.no_graph},
+            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
+                       "samples": clocks["samples"]},
+            "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms2_total / args.steps,
+                    "h2d_bytes_per_step": engine.h2d_bytes_per_step(), "d2h_bytes_per_step": 8,
+                    "last_loss": last_loss},
+            "gpu_launches": launches, "gpu_launches_per_step": engine.launches_per_step,
+            "final_global_step": info.global_step,
+        }
+        print(json.dumps(out))
+    sys.stdout.flush()
+    backend.close()
+    shutdown_context(ctx)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

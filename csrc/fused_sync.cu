@@ -65,6 +65,7 @@ struct SyncCtrl {
   uint32_t pad1[32];
   unsigned long long t_arrive[TIMING_RING];   // %globaltimer at arrival, per local step (cdf telemetry)
   unsigned long long t_start[TIMING_RING];    // %globaltimer stamped by the step's first kernel
+  unsigned long long t_phase[8];              // last launch: kernel start, decided, reduced, pushed, landed, shadowed
 };
 
 struct SyncPeers {
@@ -125,11 +126,12 @@ template <class Pred>
 DMNIST_DEVICE bool spin_until(Pred pred, unsigned long long timeout_ns) {
   if (pred()) return true;
   const unsigned long long t0 = globaltimer_ns();
-  unsigned ns = 32;
+  unsigned spins = 0;
   while (!pred()) {
-    __nanosleep(ns);
-    if (ns < 256) ns *= 2;
-    if (globaltimer_ns() - t0 > timeout_ns) return false;
+    if (++spins > 64) {          // busy-poll first (the common wait is a few microseconds), then back off
+      __nanosleep(64);
+      if ((spins & 255) == 0 && globaltimer_ns() - t0 > timeout_ns) return false;
+    }
   }
   return true;
 }
@@ -142,8 +144,9 @@ DMNIST_DEVICE void decide(const SyncPeers& P, const SyncArgs& a, SyncCtrl* me, u
   const int lane = threadIdx.x;
   const uint32_t full_mask = (a.nranks >= 32) ? 0xffffffffu : ((1u << a.nranks) - 1u);
   uint32_t mask = full_mask, late = 0, target = epoch + 1;
-  if (lane == 0) me->t_arrive[epoch % TIMING_RING] = globaltimer_ns();
-  __threadfence_system();   // my gradient arena (written by the backward kernels) is visible system-wide
+  if (lane == 0) { const unsigned long long now = globaltimer_ns(); me->t_arrive[epoch % TIMING_RING] = now; me->t_phase[0] = now; }
+  // The gradient arena was written by earlier kernels of this stream: it is complete in my L2, which is
+  // where peers read it over NVLink; the release on the flag store below orders it for them.
   if (!KOFN) {
     if (lane < a.nranks) st_release_sys(&P.ctrl[lane]->arrive[a.rank * 32], epoch + 1);
     bool ok = true;
@@ -221,6 +224,7 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_sgd_kernel(SyncPee
     s_mask = me->decided_mask;
     s_late = me->decided_late;
     s_target = me->decided_target;
+    if (blockIdx.x == 0) me->t_phase[1] = globaltimer_ns();
   }
   __syncthreads();
   const uint32_t mask = s_mask, late = s_late;
@@ -239,26 +243,49 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_sgd_kernel(SyncPee
     for (int q = 0; q < a.nranks; ++q)
       if ((mask >> q) & 1u) contrib[nc++] = q;
     const float* wsrc = P.params[a.rank];
-    for (int i = begin + blockIdx.x * SYNC_THREADS + threadIdx.x; i < end; i += gridDim.x * SYNC_THREADS) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
+    constexpr int U = 4;
+    const int stride = gridDim.x * SYNC_THREADS;
+    for (int i0 = begin + blockIdx.x * SYNC_THREADS + threadIdx.x; i0 < end; i0 += U * stride) {
+      float4 acc[U], w[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int i = i0 + u * stride;
+        if (i < end) w[u] = *reinterpret_cast<const float4*>(wsrc + 4 * (size_t)i);
+      }
       for (int c = 0; c < nc; ++c) {
         const int q = contrib[c];
-        float4 g = ld_peer_f4(P.grads[q] + 4 * (size_t)i);
-        if (drop_thresh) {   // drop-connect: contributor q's Bernoulli mask, no 1/p rescale (reference :414-416)
-          const uint32_t sm = a.drop_seed + epoch * 0x9E3779B9u + (uint32_t)q * 0x85EBCA77u;
-          g.x = dropout_keep(sm, 4u * i + 0, drop_thresh) ? g.x : 0.f;
-          g.y = dropout_keep(sm, 4u * i + 1, drop_thresh) ? g.y : 0.f;
-          g.z = dropout_keep(sm, 4u * i + 2, drop_thresh) ? g.z : 0.f;
-          g.w = dropout_keep(sm, 4u * i + 3, drop_thresh) ? g.w : 0.f;
+        float4 g[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {   // U remote loads in flight per contributor
+          const int i = i0 + u * stride;
+          g[u] = (i < end) ? ld_peer_f4(P.grads[q] + 4 * (size_t)i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (drop_thresh) {   // drop-connect: contributor q's Bernoulli mask, no 1/p rescale (reference :414-416)
+            const uint32_t i = (uint32_t)(i0 + u * stride);
+            const uint32_t sm = a.drop_seed + epoch * 0x9E3779B9u + (uint32_t)q * 0x85EBCA77u;
+            g[u].x = dropout_keep(sm, 4u * i + 0, drop_thresh) ? g[u].x : 0.f;
+            g[u].y = dropout_keep(sm, 4u * i + 1, drop_thresh) ? g[u].y : 0.f;
+            g[u].z = dropout_keep(sm, 4u * i + 2, drop_thresh) ? g[u].z : 0.f;
+            g[u].w = dropout_keep(sm, 4u * i + 3, drop_thresh) ? g[u].w : 0.f;
+          }
+          acc[u].x += g[u].x; acc[u].y += g[u].y; acc[u].z += g[u].z; acc[u].w += g[u].w;
+        }
       }
-      float4 w = *reinterpret_cast<const float4*>(wsrc + 4 * (size_t)i);
-      w.x -= scale * acc.x; w.y -= scale * acc.y; w.z -= scale * acc.z; w.w -= scale * acc.w;
-      for (int q = 0; q < a.nranks; ++q) st_peer_f4(P.params[q] + 4 * (size_t)i, w);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * stride;
+        if (i < end) {
+          w[u].x -= scale * acc[u].x; w[u].y -= scale * acc[u].y;
+          w[u].z -= scale * acc[u].z; w[u].w -= scale * acc[u].w;
+          for (int q = 0; q < a.nranks; ++q) st_peer_f4(P.params[q] + 4 * (size_t)i, w[u]);
+        }
+      }
     }
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) me->t_phase[2] = globaltimer_ns();
 
   // ---- grid-wide: all my pushes are out -> tell every rank ------------------------------------------
   __syncthreads();
@@ -267,10 +294,8 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_sgd_kernel(SyncPee
     s_last = (atomicAdd(&me->cta_counter, 1u) == gridDim.x - 1) ? 1u : 0u;
   }
   __syncthreads();
-  if (s_last && !late && threadIdx.x < a.nranks) {
-    __threadfence_system();
-    st_release_sys(&P.ctrl[threadIdx.x]->done[a.rank * 32], epoch + 1);
-  }
+  if (s_last && !late && threadIdx.x < a.nranks) st_release_sys(&P.ctrl[threadIdx.x]->done[a.rank * 32], epoch + 1);
+  if (s_last && threadIdx.x == 0) me->t_phase[3] = globaltimer_ns();
 
   // ---- wait until every team member's shard has landed in MY arena ---------------------------------
   if (threadIdx.x < a.nranks) {
@@ -281,6 +306,7 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_sgd_kernel(SyncPee
     if (!ok) me->error = 2;
   }
   __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) me->t_phase[4] = globaltimer_ns();
 
   // ---- local bf16 shadow of the fresh weights (operand source for the tcgen05 kernels) --------------
   if (a.shadow != nullptr) {
@@ -301,6 +327,7 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_sgd_kernel(SyncPee
     me->last_late = late;
     if (late) me->dropped_steps += 1; else me->accepted_steps += 1;
     me->cta_counter = 0;
+    me->t_phase[5] = globaltimer_ns();
     me->epoch = s_target;
   }
 }
@@ -340,7 +367,7 @@ int dm_sync_ctrl_offset(const char* field) {
 #define DM_OFF(name) if (strcmp(field, #name) == 0) return (int)offsetof(SyncCtrl, name)
   DM_OFF(epoch); DM_OFF(error); DM_OFF(accepted_steps); DM_OFF(dropped_steps); DM_OFF(last_mask);
   DM_OFF(last_count); DM_OFF(last_late); DM_OFF(global_step); DM_OFF(t_arrive); DM_OFF(t_start);
-  DM_OFF(cta_counter);
+  DM_OFF(cta_counter); DM_OFF(t_phase);
 #undef DM_OFF
   return -1;
 }
@@ -365,7 +392,7 @@ int dm_fused_sync_sgd(void* const* ctrl, void* const* params, void* const* grads
   a.timeout_ns = (unsigned long long)(timeout_ms * 1e6);
   a.shadow = reinterpret_cast<__nv_bfloat16*>(shadow_bf16);
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (ctas < 1) ctas = 32;
+  if (ctas < 1) ctas = 64;
   if (k < nranks) fused_sync_sgd_kernel<true><<<ctas, SYNC_THREADS, 0, stream>>>(P, a);
   else            fused_sync_sgd_kernel<false><<<ctas, SYNC_THREADS, 0, stream>>>(P, a);
   return (int)cudaGetLastError();

@@ -1,0 +1,284 @@
+"""sm_100a compute engine: the reference convnet's training step as 11 hand-written kernels
+replayed from one CUDA graph.
+
+Step = (reference src/distributed_train.py:332 ``sess.run(apply_gradients_op)``)::
+
+    memset(small grads, loss)                              2 memset nodes
+    conv1_fwd        conv+bias+ReLU+pool (SIMT, K=25)       csrc/lenet_simt.cu
+    conv2_fwd        tcgen05 implicit GEMM + bias/ReLU/pool csrc/conv2_tc.cu
+    fc1_fwd          tcgen05 GEMM, split-K into fp32        csrc/gemm_tc.cu
+    fc2_loss         bias+ReLU+dropout, fc2, softmax-CE,
+                     accuracy, and their backward           csrc/lenet_simt.cu
+    fc1_wgrad        tcgen05 GEMM (MN-major x MN-major) -> gradient arena
+    fc1_dgrad        tcgen05 GEMM -> bf16
+    unpool2          maxpool2/ReLU2 backward + conv2 bias grad
+    conv2_wgrad      tcgen05, K = pixels, fp32 atomics -> gradient arena
+    conv2_dgrad      tcgen05
+    conv1_wgrad      maxpool1/ReLU1 backward + conv1 weight/bias grad
+    fused_sync_sgd   arrival -> mask -> NVLink reduce -> 1/count -> SGD -> push -> bf16 shadow
+
+Weights live in TF layouts in one flat fp32 arena (symmetric memory); the tensor-core
+kernels read the bf16 shadow arena the fused kernel refreshes.  Nothing on this path
+calls cuDNN, cuBLAS or NCCL.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from .engine import ComputeEngine, TorchEngine
+from .models import get_model
+from .models.lenet import dropout_seed_mix
+from .ops import gemm as G
+from .ops.lib import check, load, ptr, stream_ptr
+from .parallel.backends import StepInfo
+from .parallel.fused import FusedBackend
+
+
+class CudaLeNetEngine(ComputeEngine):
+    def __init__(self, batch_size: int, backend: FusedBackend, seed: int = 66478, rank: int = 0,
+                 keep_prob: float = 0.5, use_graph: bool = True):
+        self.lib = load()
+        self.backend = backend
+        self.device = backend.ctx.device
+        self.spec, _ = get_model("lenet")
+        self.batch_size = B = batch_size
+        self.seed, self.rank, self.keep_prob = seed, rank, keep_prob
+        self.use_graph = use_graph
+        dev = self.device
+        self.params = backend.allocate(self.spec.arena_numel)
+        self.params.copy_(self.spec.init_flat(seed).to(dev))
+        self.grads = backend.allocate(self.spec.arena_numel)
+        self.shadow = backend.attach_shadow(self.params)
+        self.p = self.spec.views(self.params)
+        self.g = self.spec.views(self.grads)
+        self.pb = self.spec.views(self.shadow)
+        bf, u8, f32 = torch.bfloat16, torch.uint8, torch.float32
+        # two input slots so the H2D copy of step i+1 overlaps the compute of step i
+        self.images = [torch.zeros(B, 28, 28, dtype=f32, device=dev) for _ in range(2)]
+        self.labels = [torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(2)]
+        self.h_images = [torch.zeros(B, 28, 28, dtype=f32).pin_memory() for _ in range(2)]
+        self.h_labels = [torch.zeros(B, dtype=torch.int64).pin_memory() for _ in range(2)]
+        self.a1 = torch.zeros(B, 14, 14, 32, dtype=bf, device=dev)
+        self.code1 = torch.zeros(B, 14, 14, 32, dtype=u8, device=dev)
+        self.a2 = torch.zeros(B, 3136, dtype=bf, device=dev)
+        self.code2 = torch.zeros(B, 3136, dtype=u8, device=dev)
+        self.h_pre = torch.zeros(B, 512, dtype=f32, device=dev)
+        self.dh = torch.zeros(B, 512, dtype=bf, device=dev)
+        self.dxfc = torch.zeros(B, 3136, dtype=bf, device=dev)
+        self.dy2 = torch.zeros(B, 14, 14, 64, dtype=bf, device=dev)
+        self.dx1 = torch.zeros(B, 14, 14, 32, dtype=bf, device=dev)
+        self.d_loss_acc = torch.zeros(2, dtype=f32, device=dev)
+        self.h_loss_bufs = [torch.zeros(2, dtype=f32).pin_memory() for _ in range(2)]
+        self.h_loss_acc = self.h_loss_bufs[0]
+        self._loss_reads = 0
+        self._slot = 0            # input slot the next step computes from
+        self._loaded = 0
+        self._h2d_bytes = B * 784 * 4 + B * 8
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self._copy_done = [torch.cuda.Event() for _ in range(2)]
+        self._slot_free = [torch.cuda.Event() for _ in range(2)]
+        self._graphs = [None, None]
+        self._opt_args: Optional[dict] = None
+        self._straggler = None
+        self._stamp = False
+        p_fc1 = self.spec.param("fc1_weights")
+        self._zero_ranges = [(0, p_fc1.offset), (p_fc1.offset + p_fc1.numel, self.spec.arena_numel)]
+        self._seed_mix0 = dropout_seed_mix(seed, 0, rank)
+        self._epoch_ptr = ctypes.c_void_p(backend.ctrl.local_ptr + backend._off["epoch"])
+        self.launches_per_step = 0
+
+    # ---- inputs ------------------------------------------------------------------------------
+    def load_batch(self, images, labels) -> None:
+        """Pinned host staging -> device slot, on the copy stream (overlaps the previous step)."""
+        s = self._loaded & 1
+        hi, hl = self.h_images[s], self.h_labels[s]
+        if isinstance(images, np.ndarray):
+            hi.copy_(torch.from_numpy(images).view(self.batch_size, 28, 28))
+            hl.copy_(torch.from_numpy(labels))
+        else:
+            hi.copy_(images.reshape(self.batch_size, 28, 28))
+            hl.copy_(labels)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self._slot_free[s])   # the step that last read this slot is done
+            self.images[s].copy_(hi, non_blocking=True)
+            self.labels[s].copy_(hl, non_blocking=True)
+            self._copy_done[s].record(self.copy_stream)
+        self._slot = s
+        self._loaded += 1
+
+    def h2d_bytes_per_step(self) -> int:
+        return self._h2d_bytes
+
+    # ---- optimizer binding ------------------------------------------------------------------------
+    def attach_optimizer(self, opt) -> None:
+        """Bind the aggregation policy so the whole step (compute + fused sync) is one graph."""
+        sched = opt.lr_schedule
+        k = getattr(opt, "replicas_to_aggregate", opt.total_num_replicas)
+        self._opt_args = dict(k=int(k), lr0=float(sched.initial_learning_rate), decay_rate=float(sched.decay_rate),
+                              decay_steps=int(sched.decay_steps))
+        if getattr(opt, "drop_connect_probability", None) is not None:
+            self.backend.drop_connect_(self.grads, opt.drop_connect_probability, 0)
+        self._straggler = getattr(opt, "_straggler", None)
+        self._stamp = getattr(opt, "mode", "") == "cdf"
+        self._graphs = [None, None]
+
+    def params_updated(self) -> None:
+        """Parameters were written from the host (init / restore): refresh the bf16 shadow."""
+        self.backend.refresh_shadow(self.params)
+
+    # ---- kernel sequence ------------------------------------------------------------------------------
+    def _launch_forward(self, images: torch.Tensor, labels: torch.Tensor, B: int, train: bool,
+                        logits_out: Optional[torch.Tensor] = None) -> int:
+        lib, sp, p, pb = self.lib, stream_ptr(), self.p, self.pb
+        check(lib.dm_conv1_fwd(ptr(images), ptr(p["conv1_weights"]), ptr(p["conv1_biases"]), ptr(self.a1),
+                               ptr(self.code1), B, sp), "conv1_fwd")
+        check(lib.dm_conv2_fwd(ptr(self.a1), ptr(pb["conv2_weights"]), ptr(p["conv2_biases"]), ptr(self.a2),
+                               ptr(self.code2), B, sp), "conv2_fwd")
+        # fc1: h_pre[B,512] += a2[B,3136] (K-major) * W1[3136,512] (MN-major); split-K over 16 CTAs per tile
+        G.gemm_bf16_raw(self.a2, pb["fc1_weights"], self.h_pre, B, 512, 3136, 3136, 512, 512, False, True,
+                        G.EPI_ATOMIC_F32, splits=16, bn=128)
+        check(lib.dm_fc2_loss(ptr(self.h_pre), ptr(p["fc1_biases"]), ptr(p["fc2_weights"]), ptr(p["fc2_biases"]),
+                              ptr(labels), ptr(self.dh), ptr(self.g["fc2_weights"]), ptr(self.g["fc2_biases"]),
+                              ptr(self.g["fc1_biases"]), ptr(self.d_loss_acc), ptr(logits_out), B, int(train), 1,
+                              ctypes.c_uint(self._seed_mix0), self._epoch_ptr if train else ctypes.c_void_p(0),
+                              ctypes.c_float(self.keep_prob), sp), "fc2_loss")
+        return 4
+
+    def _launch_backward(self, images: torch.Tensor, B: int) -> int:
+        lib, sp, g, pb = self.lib, stream_ptr(), self.g, self.pb
+        # fc1 wgrad: dW1[3136,512] = a2^T (A MN-major) * dh (B MN-major), K = batch; straight into the arena
+        G.gemm_bf16_raw(self.a2, self.dh, g["fc1_weights"], 3136, 512, B, 3136, 512, 512, True, True,
+                        G.EPI_STORE_F32, bn=128)
+        # fc1 dgrad: dxfc[B,3136] = dh[B,512] (K-major) * W1[3136,512] (rows = in, K = out contiguous)
+        G.gemm_bf16_raw(self.dh, pb["fc1_weights"], self.dxfc, B, 3136, 512, 512, 512, 3136, False, False,
+                        G.EPI_STORE_BF16, bn=64)
+        check(lib.dm_unpool2(ptr(self.dxfc), ptr(self.code2), ptr(self.dy2), ptr(g["conv2_biases"]), B, sp), "unpool2")
+        check(lib.dm_conv2_wgrad(ptr(self.a1), ptr(self.dy2), ptr(g["conv2_weights"]), B, sp), "conv2_wgrad")
+        check(lib.dm_conv2_dgrad(ptr(self.dy2), ptr(pb["conv2_weights"]), ptr(self.dx1), B, sp), "conv2_dgrad")
+        check(lib.dm_conv1_wgrad(ptr(images), ptr(self.dx1), ptr(self.code1), ptr(g["conv1_weights"]),
+                                 ptr(g["conv1_biases"]), B, sp), "conv1_wgrad")
+        return 6
+
+    def _launch_zero(self) -> int:
+        sp = stream_ptr()
+        base = self.grads.data_ptr()
+        for (a, b) in self._zero_ranges:
+            check(self.lib.dm_memset_async(ctypes.c_void_p(base + 4 * a), 0, ctypes.c_ulonglong(4 * (b - a)), sp), "memset")
+        check(self.lib.dm_memset_async(ptr(self.d_loss_acc), 0, ctypes.c_ulonglong(8), sp), "memset")
+        return 0
+
+    def _launch_step(self, slot: int, with_sync: bool) -> None:
+        n = 0
+        if self._stamp:
+            self.backend.enqueue_stamp_start()
+            n += 1
+        n += self._launch_zero()
+        n += self._launch_forward(self.images[slot], self.labels[slot], self.batch_size, True)
+        n += self._launch_backward(self.images[slot], self.batch_size)
+        if with_sync:
+            if self._straggler is not None:
+                self.backend.enqueue_straggler_delay(self._straggler.prob, self._straggler.usec)
+                n += 1
+            self.backend.enqueue(self.params, self.grads, **self._opt_args)
+            n += 1
+        self.launches_per_step = n
+
+    def _run(self, with_sync: bool) -> None:
+        s = self._slot
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._copy_done[s])
+        if self.use_graph:
+            key = s
+            if self._graphs[key] is None or self._graphs[key][1] != with_sync:
+                self._launch_step(s, False)           # warm-up (gradients only): sets func attributes outside capture
+                torch.cuda.synchronize()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=torch.cuda.Stream(device=self.device)):
+                    self._launch_step(s, with_sync)
+                self._graphs[key] = (gr, with_sync)
+            self._graphs[key][0].replay()
+        else:
+            self._launch_step(s, with_sync)
+        self._slot_free[s].record(cur)
+
+    # ---- public step API ----------------------------------------------------------------------------------
+    def forward_backward(self, step: int) -> None:
+        """Gradients only (the aggregation is launched separately by the optimizer)."""
+        self._run(with_sync=False)
+
+    def train_step(self) -> None:
+        """Whole step incl. the fused allreduce+SGD kernel, as one CUDA graph replay."""
+        assert self._opt_args is not None, "attach_optimizer() first"
+        self._run(with_sync=True)
+
+    def read_loss_async(self):
+        """Queue the device->host copy of (loss, accuracy) into a pinned buffer (two alternate).
+        Returns ``(event, buffer)``: wait on the event, then read ``buffer[0]`` / ``buffer[1]``."""
+        buf = self.h_loss_bufs[self._loss_reads & 1]
+        self._loss_reads += 1
+        buf.copy_(self.d_loss_acc, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.h_loss_acc = buf
+        return ev, buf
+
+    def loss_acc(self) -> Tuple[float, float]:
+        ev, buf = self.read_loss_async()
+        ev.synchronize()
+        return float(buf[0]), float(buf[1])
+
+    def step_info(self) -> StepInfo:
+        info = self.backend.last_step_info()
+        self.backend.check_error()
+        return info
+
+    # ---- inference ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def evaluate(self, images, labels) -> Tuple[float, float]:
+        if isinstance(images, np.ndarray):
+            images, labels = torch.from_numpy(np.ascontiguousarray(images)), torch.from_numpy(np.ascontiguousarray(labels))
+        images = images.reshape(-1, 28, 28).to(self.device, torch.float32)
+        labels = labels.to(self.device, torch.int64)
+        n, B = images.shape[0], self.batch_size
+        tot_loss = tot_hit = 0.0
+        for s in range(0, n, B):
+            m = min(B, n - s)
+            self.d_loss_acc.zero_()
+            self._launch_forward(images[s:s + m].contiguous(), labels[s:s + m].contiguous(), m, False)
+            la = self.d_loss_acc.cpu()
+            tot_loss += float(la[0]) * m      # kernel scales by 1/m
+            tot_hit += float(la[1]) * m
+        return tot_loss / n, tot_hit / n
+
+    def forward_logits(self, images: torch.Tensor, labels: torch.Tensor, train: bool) -> torch.Tensor:
+        """Debug/test helper: logits of one batch through the CUDA forward."""
+        B = images.shape[0]
+        out = torch.zeros(B, 10, dtype=torch.float32, device=self.device)
+        self.d_loss_acc.zero_()
+        self._launch_forward(images.reshape(B, 28, 28).contiguous(), labels, B, train, logits_out=out)
+        return out
+
+
+def make_cuda_engine(flags, ctx, backend) -> ComputeEngine:
+    if not isinstance(backend, FusedBackend):
+        raise RuntimeError("the sm_100a engine needs the fused backend")
+    if flags.model == "lenet":
+        return CudaLeNetEngine(flags.batch_size, backend, seed=flags.seed, rank=ctx.rank,
+                               keep_prob=flags.dropout_keep_prob, use_graph=flags.use_cuda_graph)
+    # MLP families: tcgen05 GEMM engine is not wired yet; torch compute feeding the fused aggregation kernel.
+    return TorchEngine(flags.model, flags.batch_size, ctx.device, backend.allocate, seed=flags.seed, rank=ctx.rank,
+                       keep_prob=flags.dropout_keep_prob, mlp_hidden=flags.mlp_hidden,
+                       autocast_bf16=(flags.compute_dtype == "bf16"))
+
+
+def make_cuda_eval_engine(flags, device: torch.device) -> ComputeEngine:
+    from .parallel.context import ReplicaContext
+    ctx = ReplicaContext(0, 1, device.index or 0, device, "none")
+    backend = FusedBackend(ctx)
+    if flags.model == "lenet":
+        return CudaLeNetEngine(1000, backend, seed=flags.seed, keep_prob=flags.dropout_keep_prob, use_graph=False)
+    return TorchEngine(flags.model, 1, device, backend.allocate, seed=flags.seed, mlp_hidden=flags.mlp_hidden)

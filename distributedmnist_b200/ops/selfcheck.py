@@ -1,0 +1,196 @@
+"""Numerics self-checks of the sm_100a LeNet kernels against plain PyTorch fp32 references.
+
+Each check returns ``(name, error, tolerance)``; ``tests/test_lenet_kernels_gpu.py``
+asserts on them and ``tools/gpu_diag_lenet.py`` prints them all (one GPU call gives the
+full picture when bringing a kernel up).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from ..models import dropout_keep_mask, dropout_seed_mix, get_model, lenet_forward, loss_and_accuracy
+from ..parallel.context import ReplicaContext
+from ..parallel.fused import FusedBackend
+from .lib import check, load, ptr, stream_ptr
+
+Result = Tuple[str, float, float]
+
+
+def _bf(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.bfloat16)
+
+
+def _nchw(t: torch.Tensor) -> torch.Tensor:
+    return t.float().permute(0, 3, 1, 2).contiguous()
+
+
+def _nhwc(t: torch.Tensor) -> torch.Tensor:
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def _decode_pool(code: torch.Tensor):
+    return (code & 3).long(), ((code >> 2) & 1).bool()
+
+
+def check_conv1_fwd(B: int = 8, seed: int = 0) -> List[Result]:
+    lib, dev = load(), "cuda"
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = (torch.rand(B, 28, 28, generator=g) - 0.5).to(dev)
+    w = (torch.randn(5, 5, 1, 32, generator=g) * 0.1).to(dev)
+    b = (torch.randn(32, generator=g) * 0.1).to(dev)
+    out = torch.zeros(B, 14, 14, 32, dtype=torch.bfloat16, device=dev)
+    code = torch.zeros(B, 14, 14, 32, dtype=torch.uint8, device=dev)
+    check(lib.dm_conv1_fwd(ptr(x), ptr(w), ptr(b), ptr(out), ptr(code), B, stream_ptr()), "conv1_fwd")
+    conv = F.conv2d(x[:, None], w.permute(3, 2, 0, 1), b, padding=2)
+    ref = _nhwc(F.max_pool2d(F.relu(conv), 2, 2))
+    err = (out.float() - ref).abs().max().item()
+    # argmax code: the selected position must hold the window maximum
+    idx, act = _decode_pool(code)
+    win = _nhwc(conv).reshape(B, 14, 2, 14, 2, 32).permute(0, 1, 3, 5, 2, 4).reshape(B, 14, 14, 32, 4)
+    sel = torch.gather(win, 4, idx[..., None])[..., 0]
+    err_idx = (sel - win.max(dim=4).values).abs().max().item()
+    err_act = ((sel > 0) != act).float().sum().item()
+    return [("conv1_fwd.out", err, 0.02), ("conv1_fwd.argmax", err_idx, 1e-5), ("conv1_fwd.relu_flag", err_act, 0.5)]
+
+
+def check_conv2_fwd(B: int = 8, seed: int = 1) -> List[Result]:
+    lib, dev = load(), "cuda"
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    a1 = _bf(torch.rand(B, 14, 14, 32, generator=g)).to(dev)
+    w = _bf(torch.randn(5, 5, 32, 64, generator=g) * 0.05).to(dev)
+    b = (torch.randn(64, generator=g) * 0.1).to(dev)
+    out = torch.zeros(B, 7, 7, 64, dtype=torch.bfloat16, device=dev)
+    code = torch.zeros(B, 7, 7, 64, dtype=torch.uint8, device=dev)
+    check(lib.dm_conv2_fwd(ptr(a1), ptr(w), ptr(b), ptr(out), ptr(code), B, stream_ptr()), "conv2_fwd")
+    conv = F.conv2d(_nchw(a1), w.float().permute(3, 2, 0, 1), b, padding=2)
+    ref = _nhwc(F.max_pool2d(F.relu(conv), 2, 2))
+    err = (out.float() - ref).abs().max().item()
+    idx, act = _decode_pool(code)
+    win = _nhwc(conv).reshape(B, 7, 2, 7, 2, 64).permute(0, 1, 3, 5, 2, 4).reshape(B, 7, 7, 64, 4)
+    sel = torch.gather(win, 4, idx[..., None])[..., 0]
+    err_idx = (sel - win.max(dim=4).values).abs().max().item()
+    bad_act = ((sel > 1e-3) & ~act) | ((sel < -1e-3) & act)
+    return [("conv2_fwd.out", err, 0.05), ("conv2_fwd.argmax", err_idx, 2e-3),
+            ("conv2_fwd.relu_flag", bad_act.float().sum().item(), 0.5)]
+
+
+def check_conv2_dgrad(B: int = 8, seed: int = 2) -> List[Result]:
+    lib, dev = load(), "cuda"
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    dy = _bf(torch.randn(B, 14, 14, 64, generator=g) * 0.1).to(dev)
+    w = _bf(torch.randn(5, 5, 32, 64, generator=g) * 0.05).to(dev)
+    dx = torch.zeros(B, 14, 14, 32, dtype=torch.bfloat16, device=dev)
+    check(lib.dm_conv2_dgrad(ptr(dy), ptr(w), ptr(dx), B, stream_ptr()), "conv2_dgrad")
+    ref = _nhwc(torch.nn.grad.conv2d_input((B, 32, 14, 14), w.float().permute(3, 2, 0, 1), _nchw(dy), padding=2))
+    return [("conv2_dgrad", (dx.float() - ref).abs().max().item(), 0.03)]
+
+
+def check_conv2_wgrad(B: int = 8, seed: int = 3) -> List[Result]:
+    lib, dev = load(), "cuda"
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    a1 = _bf(torch.rand(B, 14, 14, 32, generator=g)).to(dev)
+    dy = _bf(torch.randn(B, 14, 14, 64, generator=g) * 0.1).to(dev)
+    gw = torch.zeros(5, 5, 32, 64, dtype=torch.float32, device=dev)
+    check(lib.dm_conv2_wgrad(ptr(a1), ptr(dy), ptr(gw), B, stream_ptr()), "conv2_wgrad")
+    ref = torch.nn.grad.conv2d_weight(_nchw(a1), (64, 32, 5, 5), _nchw(dy), padding=2).permute(2, 3, 1, 0)
+    scale = ref.abs().max().item()
+    return [("conv2_wgrad(rel)", (gw - ref).abs().max().item() / scale, 2e-3)]
+
+
+def check_fc2_loss(B: int = 64, seed: int = 4) -> List[Result]:
+    lib, dev = load(), "cuda"
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    h_pre = torch.randn(B, 512, generator=g).to(dev)
+    b1 = (torch.randn(512, generator=g) * 0.1).to(dev)
+    w2 = (torch.randn(512, 10, generator=g) * 0.1).to(dev)
+    b2 = (torch.randn(10, generator=g) * 0.1).to(dev)
+    labels = torch.randint(0, 10, (B,), generator=g).to(dev)
+    mix = dropout_seed_mix(123, 7, 2)
+    step = torch.tensor([7], dtype=torch.int32, device=dev)
+    mix0 = dropout_seed_mix(123, 0, 2)
+    dh = torch.zeros(B, 512, dtype=torch.bfloat16, device=dev)
+    gw2, gb2, gb1 = (torch.zeros(512, 10, device=dev), torch.zeros(10, device=dev), torch.zeros(512, device=dev))
+    la = torch.zeros(2, device=dev)
+    logits = torch.zeros(B, 10, device=dev)
+    hp = h_pre.clone()
+    check(lib.dm_fc2_loss(ptr(hp), ptr(b1), ptr(w2), ptr(b2), ptr(labels), ptr(dh), ptr(gw2), ptr(gb2), ptr(gb1),
+                          ptr(la), ptr(logits), B, 1, 1, ctypes.c_uint(mix0), ptr(step), ctypes.c_float(0.5),
+                          stream_ptr()), "fc2_loss")
+    # reference
+    hpre = (h_pre + b1).requires_grad_(True)
+    keep = dropout_keep_mask(mix, B, 512, 0.5, device=dev)
+    h = F.relu(hpre) * keep * 2.0
+    w2r, b2r = w2.clone().requires_grad_(True), b2.clone().requires_grad_(True)
+    lg = h @ w2r + b2r
+    loss, acc = loss_and_accuracy(lg, labels)
+    loss.backward()
+    return [("fc2.logits", (logits - lg).abs().max().item(), 1e-3),
+            ("fc2.loss", abs(la[0].item() - loss.item()), 1e-4), ("fc2.acc", abs(la[1].item() - acc.item()), 1e-6),
+            ("fc2.dh", (dh.float() - hpre.grad).abs().max().item(), 2e-4 + 0.01 * hpre.grad.abs().max().item()),
+            ("fc2.g_w2", (gw2 - w2r.grad).abs().max().item(), 1e-4), ("fc2.g_b2", (gb2 - b2r.grad).abs().max().item(), 1e-5),
+            ("fc2.g_b1", (gb1 - hpre.grad.sum(0)).abs().max().item(), 1e-3),
+            ("fc2.h_pre_zeroed", hp.abs().max().item(), 0.0 + 1e-12)]
+
+
+def _engine(B: int, seed: int = 5):
+    from ..engine_cuda import CudaLeNetEngine
+    ctx = ReplicaContext(0, 1, 0, torch.device("cuda", 0), "none")
+    be = FusedBackend(ctx)
+    return CudaLeNetEngine(B, be, seed=seed, rank=0, use_graph=False), be
+
+
+def check_end_to_end(B: int = 64, seed: int = 5) -> List[Result]:
+    """Whole forward+backward through the CUDA engine vs torch autograd on the bf16-emulating reference."""
+    eng, be = _engine(B, seed)
+    spec, _ = get_model("lenet")
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = (torch.rand(B, 28, 28, 1, generator=g) - 0.5)
+    y = torch.randint(0, 10, (B,), generator=g)
+    eng.load_batch(x.numpy(), y.numpy())
+    eng.forward_backward(0)
+    torch.cuda.synchronize()
+    loss, acc = eng.loss_acc()
+    # reference on the same weights
+    flat = eng.params.detach().clone().requires_grad_(True)
+    mask = dropout_keep_mask(dropout_seed_mix(seed, 0, 0), B, 512, 0.5, device="cuda")
+    logits = lenet_forward(spec.views(flat), x.cuda(), train=True, keep_mask=mask, emulate_bf16=True)
+    rloss, racc = loss_and_accuracy(logits, y.cuda())
+    rloss.backward()
+    out: List[Result] = [("e2e.loss", abs(loss - rloss.item()), 0.02 * max(1.0, abs(rloss.item()))),
+                         ("e2e.acc", abs(acc - racc.item()), 2.0 / B + 1e-6)]
+    gv, rv = spec.views(eng.grads), spec.views(flat.grad)
+    for name in rv:
+        scale = rv[name].abs().max().item() + 1e-8
+        out.append(("e2e.grad.%s(rel)" % name, (gv[name] - rv[name]).abs().max().item() / scale, 0.06))
+    # padding of the gradient arena must stay zero (the fused kernel reduces the whole arena)
+    out.append(("e2e.grad.padding", eng.grads[~spec.valid_mask().cuda()].abs().max().item(), 1e-12))
+    return out
+
+
+def check_training_reduces_loss(B: int = 128, steps: int = 40) -> List[Result]:
+    from ..data import make_synthetic_mnist
+    from ..parallel.aggregators import SyncReplicasOptimizer
+    from ..schedule import LearningRateSchedule
+    eng, be = _engine(B, 11)
+    eng.use_graph = True
+    opt = SyncReplicasOptimizer(be, LearningRateSchedule(0.05, 1000, 1.0), 1, 1)
+    eng.attach_optimizer(opt)
+    trx, try_, _, _ = make_synthetic_mnist(B * 8, 16, seed=3)
+    losses = []
+    for s in range(steps):
+        i = (s % 8) * B
+        eng.load_batch(trx[i:i + B], try_[i:i + B])
+        eng.train_step()
+        losses.append(eng.loss_acc()[0])
+    info = eng.step_info()
+    first, last = sum(losses[:5]) / 5, sum(losses[-5:]) / 5
+    return [("train.loss_ratio(last/first)", last / first, 0.7), ("train.steps_missing", abs(info.global_step - steps), 0.5),
+            ("train.nan", float(any(l != l for l in losses)), 0.5)]
+
+
+ALL_CHECKS = [check_conv1_fwd, check_conv2_fwd, check_conv2_dgrad, check_conv2_wgrad, check_fc2_loss,
+              check_end_to_end, check_training_reduces_loss]

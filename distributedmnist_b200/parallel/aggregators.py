@@ -183,7 +183,7 @@ class TimeoutReplicasOptimizer(_AggregatorBase):
         if d > 0:
             time.sleep(d)
         if self._acc is None:
-            self._acc = torch.zeros_like(grads)
+            self._acc = self.backend.allocate(grads.numel())   # symmetric on the fused backend
         self._acc.add_(grads)
         self._acc_count += 1
         info = StepInfo(self.local_step, False, 0, 0, applied=False)

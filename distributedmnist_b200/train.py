@@ -101,8 +101,9 @@ def train(ctx: ReplicaContext, dataset, dataset_test=None, flags=FLAGS) -> Dict:
             total_num_replicas=num_workers,
             drop_connect_probability=flags.drop_connect_probability if flags.drop_connect else None,
             straggler=straggler, seed=flags.seed)
-    if hasattr(engine, "attach_optimizer"):
-        engine.attach_optimizer(opt)   # GPU path: fuses the step into one captured graph
+    fused_step = hasattr(engine, "attach_optimizer") and not flags.interval_method
+    if fused_step:
+        engine.attach_optimizer(opt)   # GPU path: compute + fused allreduce/SGD replay as one CUDA graph
 
     # Supervisor semantics: chief restores the newest checkpoint, everyone gets it.
     restored_step = 0
@@ -160,12 +161,17 @@ def train(ctx: ReplicaContext, dataset, dataset_test=None, flags=FLAGS) -> Dict:
         t0 = time.perf_counter()
         engine.load_batch(images, labels)
         t1 = time.perf_counter()
-        engine.forward_backward(opt.local_step)
-        t2 = time.perf_counter()
-        info = opt.apply_gradients(engine.params, engine.grads) if not isinstance(opt, TimeoutReplicasOptimizer) \
-            else opt.apply_gradients(engine.params, engine.grads, ctx.rank, flags.worker_times_cdf_method)
-        if info.applied and hasattr(engine, "params_updated"):
-            engine.params_updated()
+        if fused_step:
+            engine.train_step()
+            t2 = time.perf_counter()
+            info = opt._account(engine.step_info())   # device -> host read of the step's outcome
+        else:
+            engine.forward_backward(opt.local_step)
+            t2 = time.perf_counter()
+            info = opt.apply_gradients(engine.params, engine.grads) if not isinstance(opt, TimeoutReplicasOptimizer) \
+                else opt.apply_gradients(engine.params, engine.grads, ctx.rank, flags.worker_times_cdf_method)
+            if info.applied and hasattr(engine, "params_updated") and not hasattr(engine, "train_step"):
+                engine.params_updated()
         do_log = (cur_iteration % max(flags.log_every, 1) == 0)
         if do_log or flags.timeline_logging:
             loss_value, train_acc_value = engine.loss_acc()

@@ -1,0 +1,63 @@
+"""Fused allreduce+scale+SGD kernel vs `NCCL allreduce -> /N -> torch SGD`."""
+import json
+import os
+
+import pytest
+import torch
+
+from distributedmnist_b200.parallel.launcher import run_replicas
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_single_rank_is_plain_sgd():
+    from distributedmnist_b200.parallel.context import ReplicaContext
+    from distributedmnist_b200.parallel.fused import FusedBackend
+    ctx = ReplicaContext(0, 1, 0, torch.device("cuda", 0), "none")
+    be = FusedBackend(ctx)
+    n = 1 << 16
+    params, grads = be.allocate(n), be.allocate(n)
+    be.attach_shadow(params)
+    params.copy_(torch.randn(n, device="cuda"))
+    ref = params.clone()
+    for step in range(4):
+        grads.copy_(torch.randn(n, device="cuda"))
+        ref -= 0.25 * grads
+        info = be.sync_step(params, grads, 0.25, step, 1)
+        assert info.global_step == step + 1 and info.accepted and info.mask == 1 and info.count == 1
+        assert torch.allclose(params, ref, atol=1e-6)
+        assert (be.shadow.float() - params).abs().max().item() < 0.02 * params.abs().max().item()
+    # device-side LR schedule: staircase decay evaluated from the device step counter
+    be.enqueue(params, grads, 1, lr0=1.0, decay_rate=0.5, decay_steps=2)   # epoch 4 -> lr = 0.25
+    ref -= 0.25 * grads
+    torch.cuda.synchronize()
+    assert torch.allclose(params, ref, atol=1e-6)
+    be.check_error()
+
+
+@pytest.mark.multigpu
+def test_multi_rank_matches_nccl_and_masks_straggler(tmp_path):
+    n = min(torch.cuda.device_count(), 8)
+    worker = os.path.join(HERE, "_fused_worker.py")
+    codes = run_replicas([worker, str(tmp_path / "res_RANK.json"), str(1665024)], n, timeout=300,
+                         out_dir=str(tmp_path / "out"))
+    logs = "\n".join(open(os.path.join(tmp_path, "out", f)).read()[-1500:] for f in sorted(os.listdir(tmp_path / "out")))
+    assert codes == [0] * n, logs
+    res = [json.load(open(tmp_path / ("res_%d.json" % r))) for r in range(n)]
+    full_mask = (1 << n) - 1
+    for s in range(6):
+        rows = [r["full"][s] for r in res]
+        assert all(x["mask"] == full_mask and x["count"] == n and x["accepted"] for x in rows)
+        assert all(x["err"] < 1e-5 for x in rows), rows         # tolerance: reduction order only
+        assert len({x["fp"] for x in rows}) == 1                  # replicas bit-identical
+        assert all(x["shadow_err"] < 0.05 for x in rows)
+    for s in range(6):
+        rows = [r["kofn"][s] for r in res]
+        assert len({x["mask"] for x in rows}) == 1                # same contributor set everywhere
+        m = rows[0]["mask"]
+        assert bin(m).count("1") >= n - 1 and all(x["count"] == bin(m).count("1") for x in rows)
+        assert not (m >> (n - 1)) & 1                             # the delayed rank is masked out
+        assert not rows[n - 1]["accepted"] and all(rows[q]["accepted"] for q in range(n - 1))
+        assert all(x["err"] < 1e-5 for x in rows), rows         # divisor = accepted count
+        assert len({x["fp"] for x in rows}) == 1
