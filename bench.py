@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--k", type=int, default=-1, help="replicas_to_aggregate (-1 = all)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--straggler", default="", help="rank:prob:usec device-side delay injection")
+    ap.add_argument("--kernel-times", action="store_true", help="also print per-kernel device times (stderr)")
     return ap.parse_args()
 
 
@@ -223,6 +224,11 @@ def main():
     ms2_total = float(ms2.item())
     backend.check_error()
     info = engine.step_info()
+    if args.kernel_times:
+        kt = engine.time_kernels(20)
+        if rank == 0:
+            print("KERNEL_TIMES_US " + json.dumps({k: round(v, 2) for k, v in kt.items()}) + " sum=%.1f" % sum(kt.values()),
+                  file=sys.stderr)
 
     if rank == 0:
         value = n * B * args.steps / (ms_total / 1e3)

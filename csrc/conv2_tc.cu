@@ -25,8 +25,8 @@ constexpr int W_BYTES = 800 * 64 * 2;   // 102400
 // ------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------
-constexpr int FW_STAGES = 8;
-constexpr int FW_A_BYTES = 128 * 32 * 2;   // 8 KB per tap
+constexpr int FW_STAGES = 6;
+constexpr int FW_A_BYTES = 12 * 16 * 32 * 2;   // one kw-patch: 12 rows x 16 pixels x 32 ch = 12 KB (5 kh taps inside)
 struct FwSmem {
   static constexpr int A_OFF = W_BYTES;
   static constexpr int BAR_OFF = A_OFF + FW_STAGES * FW_A_BYTES;
@@ -34,7 +34,7 @@ struct FwSmem {
 };
 
 __global__ void __launch_bounds__(CV_THREADS, 1)
-conv2_fwd_kernel(const __grid_constant__ CUtensorMap tmX,   // a1 NHWC [B,14,14,32], box (32,16,8,1), 64B swizzle
+conv2_fwd_kernel(const __grid_constant__ CUtensorMap tmX,   // a1 NHWC [B,14,14,32], box (32,16,12,1), 64B swizzle
                  const __grid_constant__ CUtensorMap tmW,   // W [800][64], box (64,200), 128B swizzle
                  const float* __restrict__ bias,            // [64]
                  __nv_bfloat16* __restrict__ out,           // pooled [B,7,7,64]
@@ -71,11 +71,13 @@ conv2_fwd_kernel(const __grid_constant__ CUtensorMap tmX,   // a1 NHWC [B,14,14,
       int it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int img = t >> 1, h0 = (t & 1) * 8;
-        for (int tap = 0; tap < 25; ++tap, ++it) {
+        for (int kw = 0; kw < 5; ++kw, ++it) {
+          // one patch per horizontal tap offset: rows h0-2 .. h0+9; the five vertical taps are row offsets
+          // inside it (16 pixels = 1024 B, a multiple of the 512 B swizzle period)
           const int s = it % FW_STAGES;
           mbar_wait(&a_empty[s], ((it / FW_STAGES) & 1) ^ 1);
           mbar_expect_tx(&a_full[s], FW_A_BYTES);
-          tma_load_4d(smem + FwSmem::A_OFF + s * FW_A_BYTES, &tmX, &a_full[s], 0, tap % 5 - 2, h0 + tap / 5 - 2, img);
+          tma_load_4d(smem + FwSmem::A_OFF + s * FW_A_BYTES, &tmX, &a_full[s], 0, kw - 2, h0 - 2, img);
         }
       }
     }
@@ -87,21 +89,24 @@ conv2_fwd_kernel(const __grid_constant__ CUtensorMap tmX,   // a1 NHWC [B,14,14,
       const int buf = tl & 1;
       mbar_wait(&acc_empty[buf], ((tl >> 1) & 1) ^ 1);
       tc_fence_after_sync();
-      for (int tap = 0; tap < 25; ++tap, ++it) {
+      for (int kw = 0; kw < 5; ++kw, ++it) {
         const int s = it % FW_STAGES;
         mbar_wait(&a_full[s], (it / FW_STAGES) & 1);
         tc_fence_after_sync();
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + FwSmem::A_OFF + s * FW_A_BYTES);
-          const uint32_t b_addr = smem_u32(smem + tap * 4096);
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const uint64_t da = make_smem_desc(a_addr + 32 * k, 16, 512, SWZ_64B);      // 64 B rows, 8-row groups 512 B
-            const uint64_t db = make_smem_desc(b_addr + 2048 * k, 8192, 1024, SWZ_128B);  // 16 ci rows per step
-            umma_bf16(tmem_base + buf * 64, da, db, idesc, (tap | k) != 0);
+          for (int kh = 0; kh < 5; ++kh) {
+            const uint32_t b_addr = smem_u32(smem + (kh * 5 + kw) * 4096);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const uint64_t da = make_smem_desc(a_addr + kh * 1024 + 32 * k, 16, 512, SWZ_64B);  // 64 B rows, 8-row groups 512 B
+              const uint64_t db = make_smem_desc(b_addr + 2048 * k, 8192, 1024, SWZ_128B);      // 16 ci rows per step
+              umma_bf16(tmem_base + buf * 64, da, db, idesc, (kw | kh | k) != 0);
+            }
           }
           umma_commit(&a_empty[s]);
-          if (tap == 24) umma_commit(&acc_full[buf]);
+          if (kw == 4) umma_commit(&acc_full[buf]);
         }
         __syncwarp();
       }
@@ -180,8 +185,8 @@ conv2_fwd_kernel(const __grid_constant__ CUtensorMap tmX,   // a1 NHWC [B,14,14,
 // ------------------------------------------------------------------------------------------------------
 // dgrad
 // ------------------------------------------------------------------------------------------------------
-constexpr int DG_STAGES = 6;
-constexpr int DG_A_BYTES = 128 * 64 * 2;   // 16 KB per tap
+constexpr int DG_STAGES = 4;
+constexpr int DG_A_BYTES = 12 * 16 * 64 * 2;   // one kw-patch: 12 rows x 16 pixels x 64 ch = 24 KB
 struct DgSmem {
   static constexpr int A_OFF = W_BYTES;
   static constexpr int BAR_OFF = A_OFF + DG_STAGES * DG_A_BYTES;
@@ -189,7 +194,7 @@ struct DgSmem {
 };
 
 __global__ void __launch_bounds__(CV_THREADS, 1)
-conv2_dgrad_kernel(const __grid_constant__ CUtensorMap tmDY,  // dY NHWC [B,14,14,64], box (64,16,8,1), 128B swizzle
+conv2_dgrad_kernel(const __grid_constant__ CUtensorMap tmDY,  // dY NHWC [B,14,14,64], box (64,16,12,1), 128B swizzle
                    const __grid_constant__ CUtensorMap tmW,
                    __nv_bfloat16* __restrict__ dx,            // [B,14,14,32]
                    int num_tiles) {
@@ -224,12 +229,13 @@ conv2_dgrad_kernel(const __grid_constant__ CUtensorMap tmDY,  // dY NHWC [B,14,1
       int it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int img = t >> 1, h0 = (t & 1) * 8;
-        for (int tap = 0; tap < 25; ++tap, ++it) {
+        for (int kw = 0; kw < 5; ++kw, ++it) {
           const int s = it % DG_STAGES;
           mbar_wait(&a_empty[s], ((it / DG_STAGES) & 1) ^ 1);
           mbar_expect_tx(&a_full[s], DG_A_BYTES);
-          // dX[y,x] += dY[y - (kh-2), x - (kw-2)] * W[kh,kw]
-          tma_load_4d(smem + DgSmem::A_OFF + s * DG_A_BYTES, &tmDY, &a_full[s], 0, 2 - tap % 5, h0 + 2 - tap / 5, img);
+          // dX[y,x] += dY[y - (kh-2), x - (kw-2)] * W[kh,kw]: patch rows h0-2 .. h0+9 at column offset 2-kw;
+          // tap kh starts at patch row 4-kh
+          tma_load_4d(smem + DgSmem::A_OFF + s * DG_A_BYTES, &tmDY, &a_full[s], 0, 2 - kw, h0 - 2, img);
         }
       }
     }
@@ -241,21 +247,24 @@ conv2_dgrad_kernel(const __grid_constant__ CUtensorMap tmDY,  // dY NHWC [B,14,1
       const int buf = tl & 1;
       mbar_wait(&acc_empty[buf], ((tl >> 1) & 1) ^ 1);
       tc_fence_after_sync();
-      for (int tap = 0; tap < 25; ++tap, ++it) {
+      for (int kw = 0; kw < 5; ++kw, ++it) {
         const int s = it % DG_STAGES;
         mbar_wait(&a_full[s], (it / DG_STAGES) & 1);
         tc_fence_after_sync();
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + DgSmem::A_OFF + s * DG_A_BYTES);
-          const uint32_t b_addr = smem_u32(smem + tap * 4096);   // W[tap]: 32 ci rows x 64 co (128 B), K-major
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = make_smem_desc(a_addr + 32 * k, 16, 1024, SWZ_128B);
-            const uint64_t db = make_smem_desc(b_addr + 32 * k, 16, 1024, SWZ_128B);
-            umma_bf16(tmem_base + buf * 32, da, db, idesc, (tap | k) != 0);
+          for (int kh = 0; kh < 5; ++kh) {
+            const uint32_t b_addr = smem_u32(smem + (kh * 5 + kw) * 4096);   // W[tap]: 32 ci rows x 64 co (128 B), K-major
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = make_smem_desc(a_addr + (4 - kh) * 2048 + 32 * k, 16, 1024, SWZ_128B);
+              const uint64_t db = make_smem_desc(b_addr + 32 * k, 16, 1024, SWZ_128B);
+              umma_bf16(tmem_base + buf * 32, da, db, idesc, (kw | kh | k) != 0);
+            }
           }
           umma_commit(&a_empty[s]);
-          if (tap == 24) umma_commit(&acc_full[buf]);
+          if (kw == 4) umma_commit(&acc_full[buf]);
         }
         __syncwarp();
       }
@@ -402,7 +411,7 @@ extern "C" {
 int dm_conv2_fwd(const void* a1, const void* w_bf16, const void* bias, void* out, void* code, int B, void* stream) {
   using namespace dm;
   CUtensorMap tmX, tmW;
-  if (make_tmap_nhwc_bf16(&tmX, a1, 32, 14, 14, B, 32, 16, 8, 64)) return 101;
+  if (make_tmap_nhwc_bf16(&tmX, a1, 32, 14, 14, B, 32, 16, 12, 64)) return 101;
   if (make_tmap_2d_bf16(&tmW, w_bf16, 64, 800, 64, 64, 200, 128)) return 102;
   static bool configured = false;
   if (!configured) {
@@ -421,7 +430,7 @@ int dm_conv2_fwd(const void* a1, const void* w_bf16, const void* bias, void* out
 int dm_conv2_dgrad(const void* dy, const void* w_bf16, void* dx, int B, void* stream) {
   using namespace dm;
   CUtensorMap tmDY, tmW;
-  if (make_tmap_nhwc_bf16(&tmDY, dy, 64, 14, 14, B, 64, 16, 8, 128)) return 101;
+  if (make_tmap_nhwc_bf16(&tmDY, dy, 64, 14, 14, B, 64, 16, 12, 128)) return 101;
   if (make_tmap_2d_bf16(&tmW, w_bf16, 64, 800, 64, 64, 200, 128)) return 102;
   static bool configured = false;
   if (!configured) {

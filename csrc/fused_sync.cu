@@ -218,17 +218,31 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_sgd_kernel(SyncPee
   __shared__ uint32_t s_mask, s_late, s_target, s_last;
   const uint32_t epoch = me->epoch;   // stable for the whole launch (only the last CTA writes it, at exit)
 
-  if (blockIdx.x == 0 && threadIdx.x < 32) decide<KOFN>(P, a, me, epoch);
-  if (threadIdx.x == 0) {
-    spin_until([&] { return ld_acquire_sys(&me->decided_tag) == epoch + 1; }, a.timeout_ns * 2);
-    s_mask = me->decided_mask;
-    s_late = me->decided_late;
-    s_target = me->decided_target;
-    if (blockIdx.x == 0) me->t_phase[1] = globaltimer_ns();
+  const bool solo = a.nranks == 1;     // single replica: no arrival / commit / done protocol at all
+  if (solo) {
+    if (threadIdx.x == 0) {
+      s_mask = 1u; s_late = 0u; s_target = epoch + 1;
+      if (blockIdx.x == 0) {
+        const unsigned long long now = globaltimer_ns();
+        me->t_arrive[epoch % TIMING_RING] = now;
+        me->t_phase[0] = now;
+        me->t_phase[1] = now;
+      }
+    }
+  } else {
+    if (blockIdx.x == 0 && threadIdx.x < 32) decide<KOFN>(P, a, me, epoch);
+    if (threadIdx.x == 0) {
+      spin_until([&] { return ld_acquire_sys(&me->decided_tag) == epoch + 1; }, a.timeout_ns * 2);
+      s_mask = me->decided_mask;
+      s_late = me->decided_late;
+      s_target = me->decided_target;
+      if (blockIdx.x == 0) me->t_phase[1] = globaltimer_ns();
+    }
   }
   __syncthreads();
   const uint32_t mask = s_mask, late = s_late;
   const int count = __popc(mask);
+  int own_begin = 0, own_end = 0;   // float4 range whose shadow this rank writes in the update loop
 
   if (!late && count > 0) {
     // ---- reduce my shard over the contributors, SGD, push to every rank -------------------------
@@ -236,6 +250,8 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_sgd_kernel(SyncPee
     const int shard = (a.numel4 + count - 1) / count;
     const int begin = my_idx * shard;
     const int end = min(begin + shard, a.numel4);
+    own_begin = begin;
+    own_end = end;
     const float scale = device_lr(a, epoch) / (float)count;
     const uint32_t drop_thresh = a.drop_keep > 0.f ? (uint32_t)(a.drop_keep * 16777216.f) : 0u;
     int contrib[SYNC_MAX_RANKS];
@@ -281,6 +297,12 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_sgd_kernel(SyncPee
           w[u].x -= scale * acc[u].x; w[u].y -= scale * acc[u].y;
           w[u].z -= scale * acc[u].z; w[u].w -= scale * acc[u].w;
           for (int q = 0; q < a.nranks; ++q) st_peer_f4(P.params[q] + 4 * (size_t)i, w[u]);
+          if (a.shadow != nullptr) {   // my shard's bf16 shadow straight from registers
+            uint2 o;
+            o.x = pack_bf16x2(w[u].x, w[u].y);
+            o.y = pack_bf16x2(w[u].z, w[u].w);
+            *reinterpret_cast<uint2*>(a.shadow + 4 * (size_t)i) = o;
+          }
         }
       }
     }
@@ -290,15 +312,15 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_sgd_kernel(SyncPee
   // ---- grid-wide: all my pushes are out -> tell every rank ------------------------------------------
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    if (!solo) __threadfence_system();
     s_last = (atomicAdd(&me->cta_counter, 1u) == gridDim.x - 1) ? 1u : 0u;
   }
   __syncthreads();
-  if (s_last && !late && threadIdx.x < a.nranks) st_release_sys(&P.ctrl[threadIdx.x]->done[a.rank * 32], epoch + 1);
+  if (!solo && s_last && !late && threadIdx.x < a.nranks) st_release_sys(&P.ctrl[threadIdx.x]->done[a.rank * 32], epoch + 1);
   if (s_last && threadIdx.x == 0) me->t_phase[3] = globaltimer_ns();
 
   // ---- wait until every team member's shard has landed in MY arena ---------------------------------
-  if (threadIdx.x < a.nranks) {
+  if (!solo && threadIdx.x < a.nranks) {
     const int q = threadIdx.x;
     uint32_t need = ((mask >> q) & 1u) ? epoch + 1 : 0u;
     if (KOFN && late) need = ld_acquire_sys(&P.ctrl[0]->last_in_mask[q]);   // fast-forward: everything committed so far
@@ -312,6 +334,7 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_sgd_kernel(SyncPee
   if (a.shadow != nullptr) {
     const float* w = P.params[a.rank];
     for (int i = blockIdx.x * SYNC_THREADS + threadIdx.x; i < a.numel4; i += gridDim.x * SYNC_THREADS) {
+      if (i >= own_begin && i < own_end) continue;                       // done in the update loop
       const float4 v = __ldcv(reinterpret_cast<const float4*>(w) + i);   // bypass L1: peers just wrote it
       uint2 o;
       o.x = pack_bf16x2(v.x, v.y);

@@ -29,6 +29,7 @@ struct GemmParams {
   int num_kb;      // ceil(K / 64)
   int ldo;         // output leading dimension (elements)
   void* out;
+  long long split_stride;   // EPI_STORE_F32 with split-K: split z writes its partial tile at out + z*split_stride
 };
 
 template <int BN>
@@ -152,7 +153,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int col0 = n0 + c * 32;
       if (row < p.M) {
         if (EPI == EPI_STORE_F32) {
-          float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
+          float* o = reinterpret_cast<float*>(p.out) + (size_t)blockIdx.z * p.split_stride + (size_t)row * p.ldo + col0;
           if (col0 + 32 <= p.N && (p.ldo & 3) == 0) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
@@ -226,12 +227,14 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CU
 //   a_mn == 0: A is [M rows][K cols] (lda elements between rows);   a_mn == 1: A is [K rows][M cols].
 //   b_mn == 0: B is [N rows][K cols] (ldb);                          b_mn == 1: B is [K rows][N cols].
 //   epi: 0 store fp32, 1 atomicAdd fp32 (split-K; caller zeroes), 2 store bf16.   bn: 64 or 128.
+//   split-K without atomics: epi 0 with splits > 1 and split_stride > 0 -> partial sums at out + z*split_stride
+//   (the consumer adds the `splits` partials while loading).
 extern "C" int dm_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, int lda, int ldb, int ldo,
-                            int a_mn, int b_mn, int epi, int splits, int bn, void* stream_) {
+                            int a_mn, int b_mn, int epi, int splits, int bn, long long split_stride, void* stream_) {
   using namespace dm;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if ((bn != 64 && bn != 128) || epi < 0 || epi > 2 || splits < 1) return -1;
-  if (splits > 1 && epi != EPI_ATOMIC_F32) return -2;
+  if (splits > 1 && !(epi == EPI_ATOMIC_F32 || (epi == EPI_STORE_F32 && split_stride > 0))) return -2;
   if ((lda & 7) || (ldb & 7)) return -3;   // TMA: global strides are multiples of 16 bytes
   CUtensorMap tmA, tmB;
   int rc;
@@ -241,8 +244,8 @@ extern "C" int dm_gemm_bf16(const void* A, const void* B, void* out, int M, int 
   if (!b_mn) rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, (uint32_t)bn, 128);
   else       rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, 64, 128);
   if (rc) return 200 + rc;
-  GemmParams p{M, N, (K + GEMM_BK - 1) / GEMM_BK, ldo, out};
-  if (splits > p.num_kb) splits = p.num_kb > 0 ? p.num_kb : 1;
+  GemmParams p{M, N, (K + GEMM_BK - 1) / GEMM_BK, ldo, out, splits > 1 ? split_stride : 0};
+  if (splits > p.num_kb && epi == EPI_ATOMIC_F32) splits = p.num_kb > 0 ? p.num_kb : 1;
 #define DM_DISPATCH(BN_, EPI_) return dispatch_major<BN_, EPI_>(a_mn != 0, b_mn != 0, tmA, tmB, p, splits, stream)
   if (bn == 64) {
     if (epi == 0) DM_DISPATCH(64, 0);

@@ -16,93 +16,97 @@
 namespace dm {
 
 // =====================================================================================================
-// conv1 forward, fused.  One CTA per (image, half): 7 pooled rows x 14 pooled cols x 32 channels.
-// Work item = (pooled position, group of 8 channels): 4 conv outputs x 8 channels x 25 taps.
+// conv1 forward, fused.  One CTA per (image, pair of pooled rows): 2 x 14 pooled positions x 32 channels.
+// Work item = (pooled position, group of 8 channels): 4 conv outputs x 8 channels x 25 taps = 800 FMA,
+// fed from shared memory (12 input values + 10 weight vectors per filter row).
 // =====================================================================================================
-constexpr int C1_THREADS = 128;
+constexpr int C1_THREADS = 128;   // 112 work items + 16 idle lanes
 
 __global__ void __launch_bounds__(C1_THREADS) conv1_fwd_kernel(const float* __restrict__ images,  // [B,28,28]
                                                                const float* __restrict__ w,       // [25][32]
                                                                const float* __restrict__ bias,    // [32]
                                                                __nv_bfloat16* __restrict__ out,   // [B,14,14,32]
                                                                uint8_t* __restrict__ code) {      // [B,14,14,32]
-  __shared__ float s_img[18][32];       // input rows (14*half - 2 .. +18) with 2-pixel zero halo each side
+  __shared__ float s_img[8][32];        // input rows 4*u-2 .. 4*u+5, columns -2 .. 29 (zero halo)
   __shared__ __align__(16) float s_w[25][32];
   __shared__ float s_b[32];
-  const int b = blockIdx.x >> 1, half = blockIdx.x & 1;
-  const int row0 = half * 14 - 2;       // first input row held in smem
-  for (int i = threadIdx.x; i < 18 * 32; i += C1_THREADS) {
+  const int b = blockIdx.x / 7, u = blockIdx.x - b * 7;   // u: pooled rows 2u, 2u+1
+  const int row0 = 4 * u - 2;
+  for (int i = threadIdx.x; i < 8 * 32; i += C1_THREADS) {
     const int r = i >> 5, c = i & 31;
     const int y = row0 + r, x = c - 2;
-    s_img[r][c] = (y >= 0 && y < 28 && x >= 0 && x < 28) ? images[(size_t)b * 784 + y * 28 + x] : 0.f;
+    s_img[r][c] = (y >= 0 && y < 28 && x >= 0 && x < 28) ? __ldg(images + (size_t)b * 784 + y * 28 + x) : 0.f;
   }
-  for (int i = threadIdx.x; i < 800; i += C1_THREADS) s_w[i >> 5][i & 31] = w[i];
+  for (int i = threadIdx.x; i < 200; i += C1_THREADS)
+    reinterpret_cast<float4*>(&s_w[0][0])[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
   if (threadIdx.x < 32) s_b[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
 
-  for (int item = threadIdx.x; item < 98 * 4; item += C1_THREADS) {
-    const int cg = item & 3, pos = item >> 2;
-    const int pr = pos / 14, pc = pos - pr * 14;          // pooled row (local) / col
-    float acc[4][8];
+  const int cg = threadIdx.x & 3, pos = threadIdx.x >> 2;
+  if (pos >= 28) return;
+  const int pr = pos / 14, pc = pos - pr * 14;          // pooled row (local) / col
+  float acc[4][8];
 #pragma unroll
-    for (int p = 0; p < 4; ++p)
+  for (int p = 0; p < 4; ++p)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[p][j] = 0.f;
-    // 6x6 input patch covering the 2x2 block of conv outputs
-    float patch[6][6];
+    for (int j = 0; j < 8; ++j) acc[p][j] = 0.f;
+#pragma unroll 1
+  for (int kh = 0; kh < 5; ++kh) {
+    float r0[6], r1[6];                                   // the two input rows this filter row touches
 #pragma unroll
-    for (int r = 0; r < 6; ++r)
-#pragma unroll
-      for (int c = 0; c < 6; ++c) patch[r][c] = s_img[2 * pr + r][2 * pc + c];
-#pragma unroll
-    for (int kh = 0; kh < 5; ++kh)
-#pragma unroll
-      for (int kw = 0; kw < 5; ++kw) {
-        const float4 w0 = *reinterpret_cast<const float4*>(&s_w[kh * 5 + kw][cg * 8]);
-        const float4 w1 = *reinterpret_cast<const float4*>(&s_w[kh * 5 + kw][cg * 8 + 4]);
-        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-        for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-          for (int dx = 0; dx < 2; ++dx) {
-            const float v = patch[dy + kh][dx + kw];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[dy * 2 + dx][j] = fmaf(v, wv[j], acc[dy * 2 + dx][j]);
-          }
-      }
-    uint32_t packed[4];
-    uint8_t codes[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float m = acc[0][j];
-      int idx = 0;
-#pragma unroll
-      for (int p = 1; p < 4; ++p)
-        if (acc[p][j] > m) { m = acc[p][j]; idx = p; }
-      m += s_b[cg * 8 + j];
-      const bool active = m > 0.f;
-      codes[j] = (uint8_t)(idx | (active ? 4 : 0));
-      const float o = active ? m : 0.f;
-      if (j & 1) packed[j >> 1] = pack_bf16x2(__uint_as_float(packed[j >> 1]), o);
-      else packed[j >> 1] = __float_as_uint(o);
+    for (int c = 0; c < 6; ++c) {
+      r0[c] = s_img[2 * pr + kh][2 * pc + c];
+      r1[c] = s_img[2 * pr + kh + 1][2 * pc + c];
     }
-    const size_t o = (((size_t)b * 14 + half * 7 + pr) * 14 + pc) * 32 + cg * 8;
-    *reinterpret_cast<uint4*>(out + o) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-    *reinterpret_cast<uint2*>(code + o) =
-        make_uint2(codes[0] | (codes[1] << 8) | (codes[2] << 16) | (codes[3] << 24),
-                   codes[4] | (codes[5] << 8) | (codes[6] << 16) | (codes[7] << 24));
+#pragma unroll
+    for (int kw = 0; kw < 5; ++kw) {
+      const float4 w0 = *reinterpret_cast<const float4*>(&s_w[kh * 5 + kw][cg * 8]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&s_w[kh * 5 + kw][cg * 8 + 4]);
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] = fmaf(r0[kw], wv[j], acc[0][j]);
+        acc[1][j] = fmaf(r0[kw + 1], wv[j], acc[1][j]);
+        acc[2][j] = fmaf(r1[kw], wv[j], acc[2][j]);
+        acc[3][j] = fmaf(r1[kw + 1], wv[j], acc[3][j]);
+      }
+    }
   }
+  uint32_t packed[4];
+  uint32_t cd[2] = {0u, 0u};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float m = acc[0][j];
+    uint32_t idx = 0;
+#pragma unroll
+    for (int p = 1; p < 4; ++p)
+      if (acc[p][j] > m) { m = acc[p][j]; idx = p; }
+    m += s_b[cg * 8 + j];
+    const bool active = m > 0.f;
+    cd[j >> 2] |= (idx | (active ? 4u : 0u)) << ((j & 3) * 8);
+    const float o = active ? m : 0.f;
+    if (j & 1) packed[j >> 1] = pack_bf16x2(__uint_as_float(packed[j >> 1]), o);
+    else packed[j >> 1] = __float_as_uint(o);
+  }
+  const size_t o = (((size_t)b * 14 + 2 * u + pr) * 14 + pc) * 32 + cg * 8;
+  *reinterpret_cast<uint4*>(out + o) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  *reinterpret_cast<uint2*>(code + o) = make_uint2(cd[0], cd[1]);
 }
 
 // =====================================================================================================
-// fc2 + softmax cross entropy + accuracy, forward and backward.  One warp per batch row.
+// fc2 + softmax cross entropy + accuracy, forward and backward.
+// CTA = 8 batch rows.  Phase 1: one warp per row (fc1 epilogue: sum the split-K partials, bias, ReLU,
+// dropout; fc2; softmax; loss; dlogits).  Phase 2: one thread per hidden unit (fc2 weight gradient over
+// the CTA's rows, d(fc1 pre-activation), fc1 bias gradient).  No shared-memory atomics anywhere.
 // =====================================================================================================
-constexpr int FC2_WARPS = 8;
+constexpr int FC2_ROWS = 8;
 constexpr int HID = 512;
 constexpr int NCLS = 10;
 
 struct Fc2Args {
-  float* h_pre;              // [B,512] fc1 accumulator (no bias); zeroed after use when zero_h_pre
+  const float* h_part;       // [splits][B,512] fc1 split-K partial accumulators (no bias)
+  long long part_stride;     // elements between partials
+  int splits;
   const float* b1;           // [512]
   const float* w2;           // [512][10]
   const float* b2;           // [10]
@@ -115,52 +119,54 @@ struct Fc2Args {
   float* logits_out;         // optional [B,10]
   int B;
   int train;
-  int zero_h_pre;
-  uint32_t seed_mix;         // dropout_seed_mix(seed, step, rank) - step added on device from *step_ptr
+  uint32_t seed_mix;         // dropout_seed_mix(seed, 0, rank); the step is added on the device
   const uint32_t* step_ptr;  // device-resident step counter (CUDA-graph friendly), may be null
   float keep_prob;
   float inv_batch;           // 1 / (rows that make up the mean)
 };
 
-__global__ void __launch_bounds__(FC2_WARPS * 32) fc2_loss_kernel(Fc2Args a) {
-  __shared__ float s_w2[HID * NCLS];
-  __shared__ float s_b1[HID];
-  __shared__ float s_gw2[HID * NCLS];
-  __shared__ float s_gb1[HID];
-  __shared__ float s_gb2[NCLS];
-  for (int i = threadIdx.x; i < HID * NCLS; i += blockDim.x) { s_w2[i] = a.w2[i]; s_gw2[i] = 0.f; }
-  for (int i = threadIdx.x; i < HID; i += blockDim.x) { s_b1[i] = a.b1[i]; s_gb1[i] = 0.f; }
-  if (threadIdx.x < NCLS) s_gb2[threadIdx.x] = 0.f;
-  __syncthreads();
-
+__global__ void __launch_bounds__(FC2_ROWS * 32) fc2_loss_kernel(Fc2Args a) {
+  __shared__ float s_h[FC2_ROWS][HID];       // post ReLU/dropout activations (0 where killed)
+  __shared__ float s_dl[FC2_ROWS][NCLS + 2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t step = a.step_ptr ? *a.step_ptr : 0u;
   const uint32_t mix = a.seed_mix + step * 0x9E3779B9u;
   const uint32_t thresh = (uint32_t)(a.keep_prob * 16777216.f);
-  const float inv_keep = 1.f / a.keep_prob;
+  const float inv_keep = a.train ? 1.f / a.keep_prob : 1.f;
+  const int row = blockIdx.x * FC2_ROWS + warp;
 
-  for (int row = blockIdx.x * FC2_WARPS + warp; row < a.B; row += gridDim.x * FC2_WARPS) {
-    float h[HID / 32];
-    float scale[HID / 32];           // d h / d pre-activation (0 when ReLU/dropout killed it)
+  // ---------------- phase 1: warp per row --------------------------------------------------------------
+  {
     float acc[NCLS];
 #pragma unroll
     for (int c = 0; c < NCLS; ++c) acc[c] = 0.f;
-    float* hp_row = a.h_pre + (size_t)row * HID;
+    if (row < a.B) {
+      // sum the split-K partials: 16 independent loads in flight per partial (not a 7-deep dependent chain)
+      float hp[HID / 32];
 #pragma unroll
-    for (int it = 0; it < HID / 32; ++it) {
-      const int j = it * 32 + lane;
-      const float hp = hp_row[j] + s_b1[j];
-      if (a.zero_h_pre) hp_row[j] = 0.f;
-      bool on = hp > 0.f;
-      float sc = 1.f;
-      if (a.train) {
-        on = on && dropout_keep(mix, (uint32_t)(row * HID + j), thresh);
-        sc = inv_keep;
+      for (int it = 0; it < HID / 32; ++it) hp[it] = a.b1[it * 32 + lane];
+      for (int s = 0; s < a.splits; ++s) {
+        const float* src = a.h_part + (size_t)s * a.part_stride + (size_t)row * HID + lane;
+#pragma unroll
+        for (int it = 0; it < HID / 32; ++it) hp[it] += src[it * 32];
       }
-      scale[it] = on ? sc : 0.f;
-      h[it] = on ? hp * sc : 0.f;
 #pragma unroll
-      for (int c = 0; c < NCLS; ++c) acc[c] = fmaf(h[it], s_w2[j * NCLS + c], acc[c]);
+      for (int it = 0; it < HID / 32; ++it) {
+        const int j = it * 32 + lane;
+        bool on = hp[it] > 0.f;
+        if (a.train) on = on && dropout_keep(mix, (uint32_t)(row * HID + j), thresh);
+        const float h = on ? hp[it] * inv_keep : 0.f;
+        s_h[warp][j] = h;
+        const float2* wr = reinterpret_cast<const float2*>(a.w2 + (size_t)j * NCLS);
+#pragma unroll
+        for (int c2 = 0; c2 < NCLS / 2; ++c2) {
+          const float2 w = __ldg(wr + c2);
+          acc[2 * c2] = fmaf(h, w.x, acc[2 * c2]);
+          acc[2 * c2 + 1] = fmaf(h, w.y, acc[2 * c2 + 1]);
+        }
+      }
+    } else {
+      for (int it = 0; it < HID / 32; ++it) s_h[warp][it * 32 + lane] = 0.f;
     }
 #pragma unroll
     for (int c = 0; c < NCLS; ++c) {
@@ -168,54 +174,65 @@ __global__ void __launch_bounds__(FC2_WARPS * 32) fc2_loss_kernel(Fc2Args a) {
       for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
       acc[c] += a.b2[c];
     }
-    const int label = (int)a.labels[row];
-    float m = acc[0];
-    int arg = 0;
+    if (row < a.B) {
+      const int label = (int)a.labels[row];
+      float m = acc[0];
+      int arg = 0;
 #pragma unroll
-    for (int c = 1; c < NCLS; ++c)
-      if (acc[c] > m) { m = acc[c]; arg = c; }
-    float p[NCLS], s = 0.f;
+      for (int c = 1; c < NCLS; ++c)
+        if (acc[c] > m) { m = acc[c]; arg = c; }
+      float p[NCLS], s = 0.f, l_label = 0.f;
 #pragma unroll
-    for (int c = 0; c < NCLS; ++c) { p[c] = __expf(acc[c] - m); s += p[c]; }
-    const float inv_s = 1.f / s;
-    float l_label = 0.f;
-#pragma unroll
-    for (int c = 0; c < NCLS; ++c) if (c == label) l_label = acc[c];
-    if (lane == 0) {
-      atomicAdd(a.loss_acc + 0, (__logf(s) - (l_label - m)) * a.inv_batch);
-      atomicAdd(a.loss_acc + 1, (arg == label ? 1.f : 0.f) * a.inv_batch);
-      if (a.logits_out)
-        for (int c = 0; c < NCLS; ++c) a.logits_out[(size_t)row * NCLS + c] = acc[c];
-    }
-    if (!a.train) continue;
-    float dl[NCLS];
-#pragma unroll
-    for (int c = 0; c < NCLS; ++c) dl[c] = (p[c] * inv_s - (c == label ? 1.f : 0.f)) * a.inv_batch;
-    if (lane < NCLS) {
-      float v = 0.f;
-#pragma unroll
-      for (int c = 0; c < NCLS; ++c) if (c == lane) v = dl[c];
-      atomicAdd(&s_gb2[lane], v);
-    }
-#pragma unroll
-    for (int it = 0; it < HID / 32; ++it) {
-      const int j = it * 32 + lane;
-      float d = 0.f;
-#pragma unroll
-      for (int c = 0; c < NCLS; ++c) {
-        d = fmaf(dl[c], s_w2[j * NCLS + c], d);
-        atomicAdd(&s_gw2[j * NCLS + c], h[it] * dl[c]);
+      for (int c = 0; c < NCLS; ++c) { p[c] = __expf(acc[c] - m); s += p[c]; if (c == label) l_label = acc[c]; }
+      const float inv_s = 1.f / s;
+      if (lane == 0) {
+        atomicAdd(a.loss_acc + 0, (__logf(s) - (l_label - m)) * a.inv_batch);
+        atomicAdd(a.loss_acc + 1, (arg == label ? 1.f : 0.f) * a.inv_batch);
       }
-      d *= scale[it];
-      a.dh[(size_t)row * HID + j] = __float2bfloat16(d);
-      atomicAdd(&s_gb1[j], d);
+#pragma unroll
+      for (int c = 0; c < NCLS; ++c)
+        if (lane == c) {
+          s_dl[warp][c] = (p[c] * inv_s - (c == label ? 1.f : 0.f)) * a.inv_batch;
+          if (a.logits_out) a.logits_out[(size_t)row * NCLS + c] = acc[c];
+        }
+    } else if (lane < NCLS) {
+      s_dl[warp][lane] = 0.f;
     }
   }
   if (!a.train) return;
   __syncthreads();
-  for (int i = threadIdx.x; i < HID * NCLS; i += blockDim.x) atomicAdd(a.g_w2 + i, s_gw2[i]);
-  for (int i = threadIdx.x; i < HID; i += blockDim.x) atomicAdd(a.g_b1 + i, s_gb1[i]);
-  if (threadIdx.x < NCLS) atomicAdd(a.g_b2 + threadIdx.x, s_gb2[threadIdx.x]);
+
+  // ---------------- phase 2: thread per hidden unit ---------------------------------------------------------
+  const int row0 = blockIdx.x * FC2_ROWS;
+  for (int j = threadIdx.x; j < HID; j += FC2_ROWS * 32) {
+    float w[NCLS], gw[NCLS];
+#pragma unroll
+    for (int c = 0; c < NCLS; ++c) { w[c] = __ldg(a.w2 + (size_t)j * NCLS + c); gw[c] = 0.f; }
+    float gb1 = 0.f;
+#pragma unroll
+    for (int r = 0; r < FC2_ROWS; ++r) {
+      const float h = s_h[r][j];
+      float d = 0.f;
+#pragma unroll
+      for (int c = 0; c < NCLS; ++c) {
+        const float dl = s_dl[r][c];
+        gw[c] = fmaf(h, dl, gw[c]);
+        d = fmaf(dl, w[c], d);
+      }
+      d = (h != 0.f) ? d * inv_keep : 0.f;      // ReLU and dropout masks: h == 0 exactly where either killed it
+      if (row0 + r < a.B) a.dh[(size_t)(row0 + r) * HID + j] = __float2bfloat16(d);
+      gb1 += d;
+    }
+#pragma unroll
+    for (int c = 0; c < NCLS; ++c) atomicAdd(a.g_w2 + (size_t)j * NCLS + c, gw[c]);
+    atomicAdd(a.g_b1 + j, gb1);
+  }
+  if (threadIdx.x < NCLS) {
+    float g = 0.f;
+#pragma unroll
+    for (int r = 0; r < FC2_ROWS; ++r) g += s_dl[r][threadIdx.x];
+    atomicAdd(a.g_b2 + threadIdx.x, g);
+  }
 }
 
 // =====================================================================================================
@@ -231,6 +248,9 @@ __global__ void __launch_bounds__(256) unpool2_kernel(const __nv_bfloat16* __res
   if (threadIdx.x < 64) s_gb[threadIdx.x] = 0.f;
   __syncthreads();
   const int total = B * 49 * 8;   // (b, pooled position, group of 8 channels)
+  float gsum[8];                  // bias-gradient partials: a thread keeps the same channel group across trips
+#pragma unroll
+  for (int j = 0; j < 8; ++j) gsum[j] = 0.f;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
     const int cg = t & 7, pos = (t >> 3) % 49, b = (t >> 3) / 49;
     const int ph = pos / 7, pw = pos - ph * 7;
@@ -249,7 +269,7 @@ __global__ void __launch_bounds__(256) unpool2_kernel(const __nv_bfloat16* __res
       const uint32_t half = (g32[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
       if (c & 4u) {
         o[c & 3u][j >> 1] |= half << ((j & 1) * 16);
-        atomicAdd(&s_gb[cg * 8 + j], __bfloat162float(__ushort_as_bfloat16((unsigned short)half)));
+        gsum[j] += __bfloat162float(__ushort_as_bfloat16((unsigned short)half));
       }
     }
 #pragma unroll
@@ -258,6 +278,16 @@ __global__ void __launch_bounds__(256) unpool2_kernel(const __nv_bfloat16* __res
       *reinterpret_cast<uint4*>(dy + (((size_t)b * 14 + y) * 14 + x) * 64 + cg * 8) =
           make_uint4(o[p][0], o[p][1], o[p][2], o[p][3]);
     }
+  }
+  // lanes l, l+8, l+16, l+24 of a warp share the channel group: fold them with two shuffles
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    gsum[j] += __shfl_xor_sync(0xffffffffu, gsum[j], 8);
+    gsum[j] += __shfl_xor_sync(0xffffffffu, gsum[j], 16);
+  }
+  if ((threadIdx.x & 31) < 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&s_gb[(threadIdx.x & 7) * 8 + j], gsum[j]);
   }
   __syncthreads();
   if (threadIdx.x < 64) atomicAdd(g_bias + threadIdx.x, s_gb[threadIdx.x]);
@@ -273,8 +303,11 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restric
                                                           float* __restrict__ g_w,                 // [25][32]
                                                           float* __restrict__ g_b,                 // [32]
                                                           int B) {
-  __shared__ float s_img[32][33];
-  __shared__ float s_red[8][26][32];
+  // Everything an image needs is staged in shared memory with wide coalesced loads first (the loop below
+  // would otherwise expose one global-load latency per pooled position).
+  __shared__ float s_img[32][34];     // row stride 34: the four argmax positions of a window hit distinct banks
+  __shared__ __align__(16) float s_g[8 * 26 * 32];     // [196][32] masked gradients; reused as [8][26][32] for the reduction
+  __shared__ __align__(8) uint8_t s_pos[196 * 32];     // argmax position code (bits 0-1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float acc[26];
 #pragma unroll
@@ -285,14 +318,25 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restric
       const int r = i >> 5, c = i & 31, y = r - 2, x = c - 2;
       s_img[r][c] = (y >= 0 && y < 28 && x >= 0 && x < 28) ? images[(size_t)b * 784 + y * 28 + x] : 0.f;
     }
+    for (int i = threadIdx.x; i < 196 * 4; i += blockDim.x) {   // 8 channels per item
+      const size_t o = (size_t)b * 6272 + (size_t)i * 8;
+      const uint4 gv = *reinterpret_cast<const uint4*>(dpool + o);
+      const uint2 cv = *reinterpret_cast<const uint2*>(code + o);
+      const uint32_t g32[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t c = ((j < 4 ? cv.x : cv.y) >> ((j & 3) * 8)) & 0xffu;
+        const float g = __bfloat162float(__ushort_as_bfloat16((unsigned short)((g32[j >> 1] >> ((j & 1) * 16)) & 0xffffu)));
+        s_g[i * 8 + j] = (c & 4u) ? g : 0.f;
+      }
+      *reinterpret_cast<uint2*>(s_pos + i * 8) = cv;
+    }
     __syncthreads();
     for (int pos = warp; pos < 196; pos += 8) {
-      const size_t o = ((size_t)b * 196 + pos) * 32 + lane;
-      const uint32_t c = code[o];
-      if (!(c & 4u)) continue;
-      const float g = __bfloat162float(dpool[o]);
+      const float g = s_g[pos * 32 + lane];
+      const uint32_t c = s_pos[pos * 32 + lane];
       const int ph = pos / 14, pw = pos - ph * 14;
-      const int y = 2 * ph + ((c >> 1) & 1), x = 2 * pw + (c & 1);   // conv-output coordinates
+      const int y = 2 * ph + ((c >> 1) & 1), x = 2 * pw + (c & 1);   // conv-output coordinates of the max
 #pragma unroll
       for (int kh = 0; kh < 5; ++kh)
 #pragma unroll
@@ -300,14 +344,15 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restric
       acc[25] += g;
     }
   }
+  __syncthreads();
 #pragma unroll
-  for (int t = 0; t < 26; ++t) s_red[warp][t][lane] = acc[t];
+  for (int t = 0; t < 26; ++t) s_g[(warp * 26 + t) * 32 + lane] = acc[t];
   __syncthreads();
   for (int i = threadIdx.x; i < 26 * 32; i += blockDim.x) {
     const int t = i >> 5, c = i & 31;
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += s_red[w][t][c];
+    for (int w = 0; w < 8; ++w) s += s_g[(w * 26 + t) * 32 + c];
     if (t < 25) atomicAdd(g_w + t * 32 + c, s);
     else atomicAdd(g_b + c, s);
   }
@@ -330,17 +375,19 @@ __global__ void bias_relu_bf16_kernel(float* __restrict__ acc, const float* __re
 extern "C" {
 
 int dm_conv1_fwd(const void* images, const void* w, const void* bias, void* out, void* code, int B, void* stream) {
-  dm::conv1_fwd_kernel<<<2 * B, dm::C1_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  dm::conv1_fwd_kernel<<<7 * B, dm::C1_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float*>(images), reinterpret_cast<const float*>(w), reinterpret_cast<const float*>(bias),
       reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<uint8_t*>(code));
   return (int)cudaGetLastError();
 }
 
-int dm_fc2_loss(void* h_pre, const void* b1, const void* w2, const void* b2, const void* labels, void* dh, void* g_w2,
-                void* g_b2, void* g_b1, void* loss_acc, void* logits_out, int B, int train, int zero_h_pre,
-                unsigned int seed_mix, const void* step_ptr, float keep_prob, void* stream) {
+int dm_fc2_loss(const void* h_part, long long part_stride, int splits, const void* b1, const void* w2, const void* b2,
+                const void* labels, void* dh, void* g_w2, void* g_b2, void* g_b1, void* loss_acc, void* logits_out,
+                int B, int train, unsigned int seed_mix, const void* step_ptr, float keep_prob, void* stream) {
   dm::Fc2Args a;
-  a.h_pre = reinterpret_cast<float*>(h_pre);
+  a.h_part = reinterpret_cast<const float*>(h_part);
+  a.part_stride = part_stride;
+  a.splits = splits;
   a.b1 = reinterpret_cast<const float*>(b1);
   a.w2 = reinterpret_cast<const float*>(w2);
   a.b2 = reinterpret_cast<const float*>(b2);
@@ -351,19 +398,18 @@ int dm_fc2_loss(void* h_pre, const void* b1, const void* w2, const void* b2, con
   a.g_b1 = reinterpret_cast<float*>(g_b1);
   a.loss_acc = reinterpret_cast<float*>(loss_acc);
   a.logits_out = reinterpret_cast<float*>(logits_out);
-  a.B = B; a.train = train; a.zero_h_pre = zero_h_pre; a.seed_mix = seed_mix;
+  a.B = B; a.train = train; a.seed_mix = seed_mix;
   a.step_ptr = reinterpret_cast<const uint32_t*>(step_ptr);
   a.keep_prob = keep_prob;
   a.inv_batch = 1.f / (float)B;
-  int grid = (B + dm::FC2_WARPS - 1) / dm::FC2_WARPS;
-  if (grid > 148) grid = 148;
-  dm::fc2_loss_kernel<<<grid, dm::FC2_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  const int grid = (B + dm::FC2_ROWS - 1) / dm::FC2_ROWS;
+  dm::fc2_loss_kernel<<<grid, dm::FC2_ROWS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   return (int)cudaGetLastError();
 }
 
 int dm_unpool2(const void* dpool, const void* code, void* dy, void* g_bias, int B, void* stream) {
   int grid = (B * 49 * 8 + 255) / 256;
-  if (grid > 148 * 4) grid = 148 * 4;
+  if (grid > 148 * 2) grid = 148 * 2;
   dm::unpool2_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(dpool), reinterpret_cast<const uint8_t*>(code),
       reinterpret_cast<__nv_bfloat16*>(dy), reinterpret_cast<float*>(g_bias), B);
@@ -371,7 +417,7 @@ int dm_unpool2(const void* dpool, const void* code, void* dy, void* g_bias, int 
 }
 
 int dm_conv1_wgrad(const void* images, const void* dpool, const void* code, void* g_w, void* g_b, int B, void* stream) {
-  int grid = B < 148 * 2 ? B : 148 * 2;
+  int grid = B < 148 ? B : 148;
   dm::conv1_wgrad_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float*>(images), reinterpret_cast<const __nv_bfloat16*>(dpool),
       reinterpret_cast<const uint8_t*>(code), reinterpret_cast<float*>(g_w), reinterpret_cast<float*>(g_b), B);

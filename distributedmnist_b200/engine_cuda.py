@@ -66,7 +66,8 @@ class CudaLeNetEngine(ComputeEngine):
         self.code1 = torch.zeros(B, 14, 14, 32, dtype=u8, device=dev)
         self.a2 = torch.zeros(B, 3136, dtype=bf, device=dev)
         self.code2 = torch.zeros(B, 3136, dtype=u8, device=dev)
-        self.h_pre = torch.zeros(B, 512, dtype=f32, device=dev)
+        self.fc1_splits = 7                                         # 49 k-blocks of 64 -> 7 per CTA
+        self.h_part = torch.zeros(self.fc1_splits, B, 512, dtype=f32, device=dev)   # fc1 split-K partial sums
         self.dh = torch.zeros(B, 512, dtype=bf, device=dev)
         self.dxfc = torch.zeros(B, 3136, dtype=bf, device=dev)
         self.dy2 = torch.zeros(B, 14, 14, 64, dtype=bf, device=dev)
@@ -95,13 +96,19 @@ class CudaLeNetEngine(ComputeEngine):
     def load_batch(self, images, labels) -> None:
         """Pinned host staging -> device slot, on the copy stream (overlaps the previous step)."""
         s = self._loaded & 1
-        hi, hl = self.h_images[s], self.h_labels[s]
-        if isinstance(images, np.ndarray):
-            hi.copy_(torch.from_numpy(images).view(self.batch_size, 28, 28))
-            hl.copy_(torch.from_numpy(labels))
+        if isinstance(images, torch.Tensor) and images.is_pinned() and labels.is_pinned() \
+                and images.dtype == torch.float32 and labels.dtype == torch.int64:
+            # already page-locked: DMA straight from the caller's buffers (they must stay untouched
+            # until the copy has run, i.e. until the step that consumes them has been enqueued twice)
+            hi, hl = images.view(self.batch_size, 28, 28), labels
         else:
-            hi.copy_(images.reshape(self.batch_size, 28, 28))
-            hl.copy_(labels)
+            hi, hl = self.h_images[s], self.h_labels[s]
+            if isinstance(images, np.ndarray):
+                hi.copy_(torch.from_numpy(images).view(self.batch_size, 28, 28))
+                hl.copy_(torch.from_numpy(labels))
+            else:
+                hi.copy_(images.reshape(self.batch_size, 28, 28))
+                hl.copy_(labels)
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self._slot_free[s])   # the step that last read this slot is done
             self.images[s].copy_(hi, non_blocking=True)
@@ -138,14 +145,17 @@ class CudaLeNetEngine(ComputeEngine):
                                ptr(self.code1), B, sp), "conv1_fwd")
         check(lib.dm_conv2_fwd(ptr(self.a1), ptr(pb["conv2_weights"]), ptr(p["conv2_biases"]), ptr(self.a2),
                                ptr(self.code2), B, sp), "conv2_fwd")
-        # fc1: h_pre[B,512] += a2[B,3136] (K-major) * W1[3136,512] (MN-major); split-K over 16 CTAs per tile
-        G.gemm_bf16_raw(self.a2, pb["fc1_weights"], self.h_pre, B, 512, 3136, 3136, 512, 512, False, True,
-                        G.EPI_ATOMIC_F32, splits=16, bn=128)
-        check(lib.dm_fc2_loss(ptr(self.h_pre), ptr(p["fc1_biases"]), ptr(p["fc2_weights"]), ptr(p["fc2_biases"]),
-                              ptr(labels), ptr(self.dh), ptr(self.g["fc2_weights"]), ptr(self.g["fc2_biases"]),
-                              ptr(self.g["fc1_biases"]), ptr(self.d_loss_acc), ptr(logits_out), B, int(train), 1,
-                              ctypes.c_uint(self._seed_mix0), self._epoch_ptr if train else ctypes.c_void_p(0),
-                              ctypes.c_float(self.keep_prob), sp), "fc2_loss")
+        # fc1: a2[B,3136] (K-major) * W1[3136,512] (MN-major), split-K: 7 partial tiles stored side by side
+        # (no atomics, nothing to zero); fc2_loss sums them while applying bias + ReLU + dropout
+        stride = self.h_part.stride(0)
+        G.gemm_bf16_raw(self.a2, pb["fc1_weights"], self.h_part, B, 512, 3136, 3136, 512, 512, False, True,
+                        G.EPI_STORE_F32, splits=self.fc1_splits, bn=64, split_stride=stride)
+        check(lib.dm_fc2_loss(ptr(self.h_part), ctypes.c_longlong(stride), self.fc1_splits, ptr(p["fc1_biases"]),
+                              ptr(p["fc2_weights"]), ptr(p["fc2_biases"]), ptr(labels), ptr(self.dh),
+                              ptr(self.g["fc2_weights"]), ptr(self.g["fc2_biases"]), ptr(self.g["fc1_biases"]),
+                              ptr(self.d_loss_acc), ptr(logits_out), B, int(train), ctypes.c_uint(self._seed_mix0),
+                              self._epoch_ptr if train else ctypes.c_void_p(0), ctypes.c_float(self.keep_prob), sp),
+              "fc2_loss")
         return 4
 
     def _launch_backward(self, images: torch.Tensor, B: int) -> int:
@@ -170,6 +180,66 @@ class CudaLeNetEngine(ComputeEngine):
             check(self.lib.dm_memset_async(ctypes.c_void_p(base + 4 * a), 0, ctypes.c_ulonglong(4 * (b - a)), sp), "memset")
         check(self.lib.dm_memset_async(ptr(self.d_loss_acc), 0, ctypes.c_ulonglong(8), sp), "memset")
         return 0
+
+    def time_kernels(self, iters: int = 20) -> dict:
+        """Average device time of every kernel of the step, measured in place with CUDA events between
+        eager launches (caches warm, as in the replayed graph; includes the launch gap)."""
+        names = ["memsets", "conv1_fwd", "conv2_fwd", "fc1_fwd", "fc2_loss", "fc1_wgrad", "fc1_dgrad", "unpool2",
+                 "conv2_wgrad", "conv2_dgrad", "conv1_wgrad", "fused_sync_sgd"]
+        tot = {n: 0.0 for n in names}
+        B, s = self.batch_size, self._slot
+        img, lbl = self.images[s], self.labels[s]
+        lib, sp, g, p, pb = self.lib, stream_ptr(), self.g, self.p, self.pb
+
+        def seq():
+            yield "memsets", lambda: self._launch_zero()
+            fw = []
+            # forward / backward are issued kernel by kernel so an event can sit between any two
+            yield "conv1_fwd", lambda: check(lib.dm_conv1_fwd(ptr(img), ptr(p["conv1_weights"]), ptr(p["conv1_biases"]),
+                                                              ptr(self.a1), ptr(self.code1), B, sp), "conv1_fwd")
+            yield "conv2_fwd", lambda: check(lib.dm_conv2_fwd(ptr(self.a1), ptr(pb["conv2_weights"]), ptr(p["conv2_biases"]),
+                                                              ptr(self.a2), ptr(self.code2), B, sp), "conv2_fwd")
+            stride = self.h_part.stride(0)
+            yield "fc1_fwd", lambda: G.gemm_bf16_raw(self.a2, pb["fc1_weights"], self.h_part, B, 512, 3136, 3136, 512, 512,
+                                                     False, True, G.EPI_STORE_F32, splits=self.fc1_splits, bn=64,
+                                                     split_stride=stride)
+            yield "fc2_loss", lambda: check(lib.dm_fc2_loss(
+                ptr(self.h_part), ctypes.c_longlong(stride), self.fc1_splits, ptr(p["fc1_biases"]), ptr(p["fc2_weights"]),
+                ptr(p["fc2_biases"]), ptr(lbl), ptr(self.dh), ptr(g["fc2_weights"]), ptr(g["fc2_biases"]),
+                ptr(g["fc1_biases"]), ptr(self.d_loss_acc), ctypes.c_void_p(0), B, 1, ctypes.c_uint(self._seed_mix0),
+                self._epoch_ptr, ctypes.c_float(self.keep_prob), sp), "fc2_loss")
+            yield "fc1_wgrad", lambda: G.gemm_bf16_raw(self.a2, self.dh, g["fc1_weights"], 3136, 512, B, 3136, 512, 512,
+                                                       True, True, G.EPI_STORE_F32, bn=128)
+            yield "fc1_dgrad", lambda: G.gemm_bf16_raw(self.dh, pb["fc1_weights"], self.dxfc, B, 3136, 512, 512, 512, 3136,
+                                                       False, False, G.EPI_STORE_BF16, bn=64)
+            yield "unpool2", lambda: check(lib.dm_unpool2(ptr(self.dxfc), ptr(self.code2), ptr(self.dy2),
+                                                          ptr(g["conv2_biases"]), B, sp), "unpool2")
+            yield "conv2_wgrad", lambda: check(lib.dm_conv2_wgrad(ptr(self.a1), ptr(self.dy2), ptr(g["conv2_weights"]), B, sp),
+                                               "conv2_wgrad")
+            yield "conv2_dgrad", lambda: check(lib.dm_conv2_dgrad(ptr(self.dy2), ptr(pb["conv2_weights"]), ptr(self.dx1), B, sp),
+                                               "conv2_dgrad")
+            yield "conv1_wgrad", lambda: check(lib.dm_conv1_wgrad(ptr(img), ptr(self.dx1), ptr(self.code1),
+                                                                  ptr(g["conv1_weights"]), ptr(g["conv1_biases"]), B, sp),
+                                               "conv1_wgrad")
+            yield "fused_sync_sgd", lambda: self.backend.enqueue(self.params, self.grads, **self._opt_args)
+
+        for it in range(iters + 3):
+            evs = [torch.cuda.Event(enable_timing=True)]
+            evs[0].record()
+            order = []
+            for name, fn in seq():
+                fn()
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                evs.append(e)
+                order.append(name)
+            torch.cuda.synchronize()
+            if self.backend.ctx.world_size > 1:
+                self.backend.barrier()
+            if it >= 3:
+                for i, name in enumerate(order):
+                    tot[name] += evs[i].elapsed_time(evs[i + 1]) * 1e3 / iters
+        return tot
 
     def _launch_step(self, slot: int, with_sync: bool) -> None:
         n = 0

@@ -38,7 +38,7 @@ class FusedBackend(Backend):
         require_blackwell(ctx.device)
         check(self.lib.dm_set_device(ctx.device.index or 0), "dm_set_device")
         import os
-        self.ctas = ctas or int(os.environ.get("DMNIST_SYNC_CTAS", "64"))
+        self.ctas = ctas or int(os.environ.get("DMNIST_SYNC_CTAS", "148"))
         self.timeout_ms = timeout_ms
         self._buffers: List[SymmetricBuffer] = []
         self._by_ptr: Dict[int, SymmetricBuffer] = {}

@@ -1,0 +1,75 @@
+"""Tooling parity on CPU: Cfg interpolation, role templating/launch, log scraping, figures
+(reference tools/tf_ec2.py:17-25,445-615 and tools/benchmark.py)."""
+import os
+import struct
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+def test_cfg_self_interpolation():
+    from cluster import Cfg
+    c = Cfg({"name": "x", "nfs": "/mnt", "base_out_dir": "%(nfs)s/%(name)s", "n": 3,
+             "cmds": ["rm -rf %(base_out_dir)s", 5]})
+    assert c["base_out_dir"] == "/mnt/x"
+    assert c["cmds"] == ["rm -rf /mnt/x", 5] and c["n"] == 3
+
+
+def test_every_shipped_cfg_loads_and_templates():
+    import glob
+
+    from benchmark import load_cfg_from_file
+    files = [f for f in glob.glob(os.path.join(ROOT, "cfg", "*", "*"))]
+    assert len(files) >= 17
+    for f in files:
+        c = load_cfg_from_file(f)
+        cmd = c["train_commands"][0]
+        assert "--num_replicas_to_aggregate=%s" % c["num_replicas_to_aggregate"] in cmd
+        assert "WORKER_HOSTS" in cmd and "ROLE_ID" in cmd and c["name"] in c["base_out_dir"]
+    ks = sorted(int(load_cfg_from_file(f)["num_replicas_to_aggregate"])
+                for f in files if f.endswith("_aggregate_sync"))
+    assert ks == [1, 2, 4, 6, 7, 8]
+
+
+def test_log_scrapers_and_stats(tmp_path):
+    import benchmark as bm
+    ev = tmp_path / "run_out_evaluator"
+    ev.write_text("Succesfully loaded model from model.ckpt-10 at step=10.\n"
+                  "Num examples: 10000  Precision @ 1: 0.912300 Loss: 0.301000 Time: 3.500000\n"
+                  "Succesfully loaded model from model.ckpt-20 at step=20.\n"
+                  "Num examples: 10000  Precision @ 1: 0.950000 Loss: 0.200000 Time: 5.000000\n")
+    t, l, p, s = bm.extract_times_losses_precision(str(ev))
+    assert (t, l, p, s) == ([3.5, 5.0], [0.301, 0.2], [0.9123, 0.95], [10, 20])
+    ms = tmp_path / "run_out_master"
+    ms.write_text("INFO:dmnist:Worker 0: 2026: step 7, loss = 1.0, train_acc = 0.5, test_acc = 0.0(1.0 examples/sec; 0.1  sec/batch)\n"
+                  "INFO:dmnist:ELAPSED TIMES [(0.01, 0, 11), (0.02, 1, 11), (0.03, 0, 12), (0.05, 1, 12)]\n"
+                  "INFO:dmnist:ITERATION TIMES [0.1, 0.2]\n")
+    assert bm.current_iteration(str(ms)) == 7
+    ct = bm.extract_compute_times(str(ms))
+    assert ct[3] == (0.05, 1, 12) and bm.extract_iteration_times(str(ms)) == [0.1, 0.2]
+    st = bm.worker_time_stats(ct)
+    assert st["max"] == 0.05 and st["mean_iter_p100"] == pytest.approx(0.035)
+    pngs = [bm.plot_time_loss(str(tmp_path), str(tmp_path)), bm.plot_time_cdfs(str(tmp_path), str(tmp_path))]
+    for png in pngs:
+        data = open(png, "rb").read()
+        assert data[:8] == b"\x89PNG\r\n\x1a\n" and struct.unpack(">II", data[16:24]) == (800, 520)
+
+
+def test_end_to_end_cpu_experiment(tmp_path):
+    """benchmark -> cluster.run_tf -> 2 gloo workers + evaluator -> logs -> figures."""
+    import benchmark as bm
+    cfg = bm.load_cfg_from_file(os.path.join(ROOT, "cfg", "cpu_plumbing", "2_workers_gloo_mlp2"))
+    cfg["base_out_dir"] = str(tmp_path / "runs" / "%(name)s")
+    cfg["max_steps"] = "40"
+    out = str(tmp_path / "result_dir")
+    figs = bm.plot_figs([cfg], n_iters=30, outdir=out, dest=str(tmp_path / "figs"))
+    master = open(os.path.join(out, "2_workers_gloo_mlp2_out_master")).read()
+    assert bm.current_iteration(os.path.join(out, "2_workers_gloo_mlp2_out_master")) >= 30, master[-2000:]
+    evaluator = open(os.path.join(out, "2_workers_gloo_mlp2_out_evaluator")).read()
+    t, l, p, s = bm.extract_times_losses_precision(os.path.join(out, "2_workers_gloo_mlp2_out_evaluator"))
+    assert len(t) >= 1 and 0.0 <= p[-1] <= 1.0, evaluator[-2000:]
+    assert all(os.path.getsize(f) > 500 for f in figs)
+    assert os.path.exists(tmp_path / "runs" / "2_workers_gloo_mlp2" / "results.txt")
