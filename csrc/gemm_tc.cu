@@ -22,7 +22,7 @@ constexpr int GEMM_BK = 64;
 constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_THREADS = 192;
 
-enum GemmEpilogue : int { EPI_STORE_F32 = 0, EPI_ATOMIC_F32 = 1, EPI_STORE_BF16 = 2 };
+enum GemmEpilogue : int { EPI_STORE_F32 = 0, EPI_ATOMIC_F32 = 1, EPI_STORE_BF16 = 2, EPI_BIAS_RELU_BF16 = 3 };
 
 struct GemmParams {
   int M, N;        // logical output extent (predication)
@@ -30,6 +30,7 @@ struct GemmParams {
   int ldo;         // output leading dimension (elements)
   void* out;
   long long split_stride;   // EPI_STORE_F32 with split-K: split z writes its partial tile at out + z*split_stride
+  const float* bias;        // EPI_BIAS_RELU_BF16: per-column bias (reference K2/K3 fused into the producer)
 };
 
 template <int BN>
@@ -169,6 +170,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 32; ++j)
             if (col0 + j < p.N) atomicAdd(o + j, __uint_as_float(v[j]));
         } else {
+          if (EPI == EPI_BIAS_RELU_BF16) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float b = (col0 + j < p.N) ? __ldg(p.bias + col0 + j) : 0.f;
+              v[j] = __float_as_uint(fmaxf(__uint_as_float(v[j]) + b, 0.f));
+            }
+          }
           __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + col0;
           if (col0 + 32 <= p.N && (p.ldo & 7) == 0) {
 #pragma unroll
@@ -230,10 +238,12 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CU
 //   split-K without atomics: epi 0 with splits > 1 and split_stride > 0 -> partial sums at out + z*split_stride
 //   (the consumer adds the `splits` partials while loading).
 extern "C" int dm_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, int lda, int ldb, int ldo,
-                            int a_mn, int b_mn, int epi, int splits, int bn, long long split_stride, void* stream_) {
+                            int a_mn, int b_mn, int epi, int splits, int bn, long long split_stride, const void* bias,
+                            void* stream_) {
   using namespace dm;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if ((bn != 64 && bn != 128) || epi < 0 || epi > 2 || splits < 1) return -1;
+  if ((bn != 64 && bn != 128) || epi < 0 || epi > 3 || splits < 1) return -1;
+  if (epi == EPI_BIAS_RELU_BF16 && bias == nullptr) return -4;
   if (splits > 1 && !(epi == EPI_ATOMIC_F32 || (epi == EPI_STORE_F32 && split_stride > 0))) return -2;
   if ((lda & 7) || (ldb & 7)) return -3;   // TMA: global strides are multiples of 16 bytes
   CUtensorMap tmA, tmB;
@@ -244,17 +254,20 @@ extern "C" int dm_gemm_bf16(const void* A, const void* B, void* out, int M, int 
   if (!b_mn) rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, (uint32_t)bn, 128);
   else       rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, 64, 128);
   if (rc) return 200 + rc;
-  GemmParams p{M, N, (K + GEMM_BK - 1) / GEMM_BK, ldo, out, splits > 1 ? split_stride : 0};
+  GemmParams p{M, N, (K + GEMM_BK - 1) / GEMM_BK, ldo, out, splits > 1 ? split_stride : 0,
+               reinterpret_cast<const float*>(bias)};
   if (splits > p.num_kb && epi == EPI_ATOMIC_F32) splits = p.num_kb > 0 ? p.num_kb : 1;
 #define DM_DISPATCH(BN_, EPI_) return dispatch_major<BN_, EPI_>(a_mn != 0, b_mn != 0, tmA, tmB, p, splits, stream)
   if (bn == 64) {
     if (epi == 0) DM_DISPATCH(64, 0);
     if (epi == 1) DM_DISPATCH(64, 1);
-    DM_DISPATCH(64, 2);
+    if (epi == 2) DM_DISPATCH(64, 2);
+    DM_DISPATCH(64, 3);
   } else {
     if (epi == 0) DM_DISPATCH(128, 0);
     if (epi == 1) DM_DISPATCH(128, 1);
-    DM_DISPATCH(128, 2);
+    if (epi == 2) DM_DISPATCH(128, 2);
+    DM_DISPATCH(128, 3);
   }
 #undef DM_DISPATCH
 }

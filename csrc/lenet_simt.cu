@@ -22,11 +22,26 @@ namespace dm {
 // =====================================================================================================
 constexpr int C1_THREADS = 128;   // 112 work items + 16 idle lanes
 
+struct ZeroRanges {
+  float* ptr[3];
+  int n[3];
+};
+
 __global__ void __launch_bounds__(C1_THREADS) conv1_fwd_kernel(const float* __restrict__ images,  // [B,28,28]
                                                                const float* __restrict__ w,       // [25][32]
                                                                const float* __restrict__ bias,    // [32]
                                                                __nv_bfloat16* __restrict__ out,   // [B,14,14,32]
-                                                               uint8_t* __restrict__ code) {      // [B,14,14,32]
+                                                               uint8_t* __restrict__ code,        // [B,14,14,32]
+                                                               ZeroRanges zr) {
+  // First kernel of a training step: also clears the gradient regions that later kernels accumulate into
+  // with atomics and the loss accumulator (replaces three memset nodes of the step graph).
+  {
+    const int gi = blockIdx.x * C1_THREADS + threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      if (zr.ptr[r] != nullptr)
+        for (int i = gi; i < zr.n[r]; i += gridDim.x * C1_THREADS) zr.ptr[r][i] = 0.f;
+  }
   __shared__ float s_img[8][32];        // input rows 4*u-2 .. 4*u+5, columns -2 .. 29 (zero halo)
   __shared__ __align__(16) float s_w[25][32];
   __shared__ float s_b[32];
@@ -45,11 +60,12 @@ __global__ void __launch_bounds__(C1_THREADS) conv1_fwd_kernel(const float* __re
   const int cg = threadIdx.x & 3, pos = threadIdx.x >> 2;
   if (pos >= 28) return;
   const int pr = pos / 14, pc = pos - pr * 14;          // pooled row (local) / col
-  float acc[4][8];
+  // packed fp32 FMA (FFMA2 on sm_100): two channels per instruction, input value broadcast to both halves
+  float2 acc2[4][4];
 #pragma unroll
   for (int p = 0; p < 4; ++p)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[p][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc2[p][j] = make_float2(0.f, 0.f);
 #pragma unroll 1
   for (int kh = 0; kh < 5; ++kh) {
     float r0[6], r1[6];                                   // the two input rows this filter row touches
@@ -62,16 +78,24 @@ __global__ void __launch_bounds__(C1_THREADS) conv1_fwd_kernel(const float* __re
     for (int kw = 0; kw < 5; ++kw) {
       const float4 w0 = *reinterpret_cast<const float4*>(&s_w[kh * 5 + kw][cg * 8]);
       const float4 w1 = *reinterpret_cast<const float4*>(&s_w[kh * 5 + kw][cg * 8 + 4]);
-      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const float2 wv[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y),
+                            make_float2(w1.z, w1.w)};
+      const float2 a00 = make_float2(r0[kw], r0[kw]), a01 = make_float2(r0[kw + 1], r0[kw + 1]);
+      const float2 a10 = make_float2(r1[kw], r1[kw]), a11 = make_float2(r1[kw + 1], r1[kw + 1]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[0][j] = fmaf(r0[kw], wv[j], acc[0][j]);
-        acc[1][j] = fmaf(r0[kw + 1], wv[j], acc[1][j]);
-        acc[2][j] = fmaf(r1[kw], wv[j], acc[2][j]);
-        acc[3][j] = fmaf(r1[kw + 1], wv[j], acc[3][j]);
+      for (int j = 0; j < 4; ++j) {
+        acc2[0][j] = __ffma2_rn(a00, wv[j], acc2[0][j]);
+        acc2[1][j] = __ffma2_rn(a01, wv[j], acc2[1][j]);
+        acc2[2][j] = __ffma2_rn(a10, wv[j], acc2[2][j]);
+        acc2[3][j] = __ffma2_rn(a11, wv[j], acc2[3][j]);
       }
     }
   }
+  float acc[4][8];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[p][2 * j] = acc2[p][j].x; acc[p][2 * j + 1] = acc2[p][j].y; }
   uint32_t packed[4];
   uint32_t cd[2] = {0u, 0u};
 #pragma unroll
@@ -374,10 +398,16 @@ __global__ void bias_relu_bf16_kernel(float* __restrict__ acc, const float* __re
 
 extern "C" {
 
-int dm_conv1_fwd(const void* images, const void* w, const void* bias, void* out, void* code, int B, void* stream) {
+// zero0/1/2 (+ counts, in floats): optional regions cleared by the kernel.
+int dm_conv1_fwd(const void* images, const void* w, const void* bias, void* out, void* code, int B, void* zero0,
+                 int n0, void* zero1, int n1, void* zero2, int n2, void* stream) {
+  dm::ZeroRanges zr;
+  zr.ptr[0] = reinterpret_cast<float*>(zero0); zr.n[0] = n0;
+  zr.ptr[1] = reinterpret_cast<float*>(zero1); zr.n[1] = n1;
+  zr.ptr[2] = reinterpret_cast<float*>(zero2); zr.n[2] = n2;
   dm::conv1_fwd_kernel<<<7 * B, dm::C1_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const float*>(images), reinterpret_cast<const float*>(w), reinterpret_cast<const float*>(bias),
-      reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<uint8_t*>(code));
+      reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<uint8_t*>(code), zr);
   return (int)cudaGetLastError();
 }
 

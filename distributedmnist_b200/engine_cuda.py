@@ -100,14 +100,14 @@ class CudaLeNetEngine(ComputeEngine):
                 and images.dtype == torch.float32 and labels.dtype == torch.int64:
             # already page-locked: DMA straight from the caller's buffers (they must stay untouched
             # until the copy has run, i.e. until the step that consumes them has been enqueued twice)
-            hi, hl = images.view(self.batch_size, 28, 28), labels
+            hi, hl = images.view(self.images[0].shape), labels
         else:
             hi, hl = self.h_images[s], self.h_labels[s]
             if isinstance(images, np.ndarray):
-                hi.copy_(torch.from_numpy(images).view(self.batch_size, 28, 28))
+                hi.copy_(torch.from_numpy(images).view(hi.shape))
                 hl.copy_(torch.from_numpy(labels))
             else:
-                hi.copy_(images.reshape(self.batch_size, 28, 28))
+                hi.copy_(images.reshape(hi.shape))
                 hl.copy_(labels)
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self._slot_free[s])   # the step that last read this slot is done
@@ -142,7 +142,7 @@ class CudaLeNetEngine(ComputeEngine):
                         logits_out: Optional[torch.Tensor] = None) -> int:
         lib, sp, p, pb = self.lib, stream_ptr(), self.p, self.pb
         check(lib.dm_conv1_fwd(ptr(images), ptr(p["conv1_weights"]), ptr(p["conv1_biases"]), ptr(self.a1),
-                               ptr(self.code1), B, sp), "conv1_fwd")
+                               ptr(self.code1), B, *self._zero_args(train), sp), "conv1_fwd")
         check(lib.dm_conv2_fwd(ptr(self.a1), ptr(pb["conv2_weights"]), ptr(p["conv2_biases"]), ptr(self.a2),
                                ptr(self.code2), B, sp), "conv2_fwd")
         # fc1: a2[B,3136] (K-major) * W1[3136,512] (MN-major), split-K: 7 partial tiles stored side by side
@@ -173,13 +173,17 @@ class CudaLeNetEngine(ComputeEngine):
                                  ptr(g["conv1_biases"]), B, sp), "conv1_wgrad")
         return 6
 
-    def _launch_zero(self) -> int:
-        sp = stream_ptr()
+    def _zero_args(self, train: bool):
+        """Regions conv1_fwd clears at the start of a training step (atomically accumulated gradients + loss)."""
+        if not train:
+            return (ctypes.c_void_p(0), 0, ctypes.c_void_p(0), 0, ptr(self.d_loss_acc), 2)
         base = self.grads.data_ptr()
-        for (a, b) in self._zero_ranges:
-            check(self.lib.dm_memset_async(ctypes.c_void_p(base + 4 * a), 0, ctypes.c_ulonglong(4 * (b - a)), sp), "memset")
-        check(self.lib.dm_memset_async(ptr(self.d_loss_acc), 0, ctypes.c_ulonglong(8), sp), "memset")
-        return 0
+        (a0, b0), (a1, b1) = self._zero_ranges
+        return (ctypes.c_void_p(base + 4 * a0), b0 - a0, ctypes.c_void_p(base + 4 * a1), b1 - a1,
+                ptr(self.d_loss_acc), 2)
+
+    def _launch_zero(self) -> int:
+        return 0    # folded into conv1_fwd
 
     def time_kernels(self, iters: int = 20) -> dict:
         """Average device time of every kernel of the step, measured in place with CUDA events between
@@ -196,7 +200,8 @@ class CudaLeNetEngine(ComputeEngine):
             fw = []
             # forward / backward are issued kernel by kernel so an event can sit between any two
             yield "conv1_fwd", lambda: check(lib.dm_conv1_fwd(ptr(img), ptr(p["conv1_weights"]), ptr(p["conv1_biases"]),
-                                                              ptr(self.a1), ptr(self.code1), B, sp), "conv1_fwd")
+                                                              ptr(self.a1), ptr(self.code1), B, *self._zero_args(True), sp),
+                                             "conv1_fwd")
             yield "conv2_fwd", lambda: check(lib.dm_conv2_fwd(ptr(self.a1), ptr(pb["conv2_weights"]), ptr(p["conv2_biases"]),
                                                               ptr(self.a2), ptr(self.code2), B, sp), "conv2_fwd")
             stride = self.h_part.stride(0)
@@ -317,7 +322,6 @@ class CudaLeNetEngine(ComputeEngine):
         tot_loss = tot_hit = 0.0
         for s in range(0, n, B):
             m = min(B, n - s)
-            self.d_loss_acc.zero_()
             self._launch_forward(images[s:s + m].contiguous(), labels[s:s + m].contiguous(), m, False)
             la = self.d_loss_acc.cpu()
             tot_loss += float(la[0]) * m      # kernel scales by 1/m
@@ -333,16 +337,157 @@ class CudaLeNetEngine(ComputeEngine):
         return out
 
 
+class CudaMlpEngine(ComputeEngine):
+    """2-/3-layer MLP on the sm_100a kernels: hidden layers = tcgen05 GEMM with bias+ReLU fused in the
+    epilogue, output layer + softmax-CE = SIMT (csrc/mlp_simt.cu), every weight gradient = tcgen05 GEMM
+    with MN-major operands writing straight into the gradient arena."""
+
+    def __init__(self, model: str, batch_size: int, backend: FusedBackend, hidden: int = 1024, seed: int = 66478,
+                 rank: int = 0, use_graph: bool = True):
+        assert hidden % 64 == 0, "--mlp_hidden must be a multiple of 64 on the GPU path"
+        self.lib, self.backend, self.device = load(), backend, backend.ctx.device
+        self.spec, _ = get_model(model, hidden)
+        self.model, self.batch_size, self.hidden = model, batch_size, hidden
+        self.n_layers = len(self.spec.params) // 2
+        self.use_graph = use_graph
+        B, dev, bf = batch_size, self.device, torch.bfloat16
+        self.params = backend.allocate(self.spec.arena_numel)
+        self.params.copy_(self.spec.init_flat(seed).to(dev))
+        self.grads = backend.allocate(self.spec.arena_numel)
+        self.shadow = backend.attach_shadow(self.params)
+        self.p, self.g, self.pb = (self.spec.views(t) for t in (self.params, self.grads, self.shadow))
+        self.images = [torch.zeros(B, 784, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.labels = [torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(2)]
+        self.h_images = [torch.zeros(B, 784, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.h_labels = [torch.zeros(B, dtype=torch.int64).pin_memory() for _ in range(2)]
+        self.x16 = torch.zeros(B, 784, dtype=bf, device=dev)
+        self.h = [torch.zeros(B, hidden, dtype=bf, device=dev) for _ in range(self.n_layers - 1)]
+        self.dh = [torch.zeros(B, hidden, dtype=bf, device=dev) for _ in range(self.n_layers - 1)]
+        self.dl_pad = torch.zeros(B, 64, dtype=bf, device=dev)
+        self.d_loss_acc = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.h_loss_bufs = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._loss_reads = 0
+        self._slot = self._loaded = 0
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self._copy_done = [torch.cuda.Event() for _ in range(2)]
+        self._slot_free = [torch.cuda.Event() for _ in range(2)]
+        self._graphs = [None, None]
+        self._opt_args: Optional[dict] = None
+        self._straggler = None
+        self.launches_per_step = 0
+        # everything except the weight matrices (written whole by GEMM stores) is accumulated with atomics
+        stored = sorted((q.offset, q.offset + q.numel) for q in self.spec.params if q.name.endswith("weights"))
+        self._zero_ranges, pos = [], 0
+        for (a0, a1) in stored:
+            if a0 > pos:
+                self._zero_ranges.append((pos, a0))
+            pos = a1
+        if pos < self.spec.arena_numel:
+            self._zero_ranges.append((pos, self.spec.arena_numel))
+
+    # shared plumbing with the convnet engine
+    load_batch = CudaLeNetEngine.load_batch
+    attach_optimizer = CudaLeNetEngine.attach_optimizer
+    params_updated = CudaLeNetEngine.params_updated
+    _run = CudaLeNetEngine._run
+    forward_backward = CudaLeNetEngine.forward_backward
+    train_step = CudaLeNetEngine.train_step
+    read_loss_async = CudaLeNetEngine.read_loss_async
+    loss_acc = CudaLeNetEngine.loss_acc
+    step_info = CudaLeNetEngine.step_info
+    _stamp = False
+
+    def h2d_bytes_per_step(self) -> int:
+        return self.batch_size * (784 * 4 + 8)
+
+    def _forward(self, images: torch.Tensor, labels: torch.Tensor, B: int, train: bool,
+                 logits_out: Optional[torch.Tensor] = None) -> int:
+        lib, sp, p, pb, H = self.lib, stream_ptr(), self.p, self.pb, self.hidden
+        n = 0
+        check(lib.dm_f32_to_bf16(ptr(images), ptr(self.x16), ctypes.c_longlong(B * 784), sp), "f32_to_bf16")
+        src, K = self.x16, 784
+        for i in range(1, self.n_layers):
+            # h_i = relu(src @ W_i + b_i): A K-major, B = W_i [in,out] MN-major, bias+ReLU in the epilogue
+            G.gemm_bf16_raw(src, pb["fc%d_weights" % i], self.h[i - 1], B, H, K, K, H, H, False, True,
+                            G.EPI_BIAS_RELU_BF16, bn=128, bias=p["fc%d_biases" % i])
+            src, K = self.h[i - 1], H
+            n += 1
+        L = self.n_layers
+        check(lib.dm_dense10_xent(ptr(src), ptr(p["fc%d_weights" % L]), ptr(p["fc%d_biases" % L]), ptr(labels),
+                                  ptr(self.dh[-1]), ptr(self.dl_pad), ptr(self.g["fc%d_biases" % L]),
+                                  ptr(self.d_loss_acc), ptr(logits_out), B, H, int(train), sp), "dense10_xent")
+        return n + 2
+
+    def _backward(self, B: int) -> int:
+        lib, sp, g, pb, H, L = self.lib, stream_ptr(), self.g, self.pb, self.hidden, self.n_layers
+        n = 0
+        # output layer: dW_L[H,10] = h_last^T (MN-major) * dl (MN-major, 64-wide zero-padded rows, N = 10)
+        G.gemm_bf16_raw(self.h[-1], self.dl_pad, g["fc%d_weights" % L], H, 10, B, H, 64, 10, True, True,
+                        G.EPI_STORE_F32, bn=64)
+        check(lib.dm_relu_bwd_colsum(ptr(self.dh[-1]), ctypes.c_void_p(0), ctypes.c_void_p(0),
+                                     ptr(g["fc%d_biases" % (L - 1)]), B, H, sp), "colsum")
+        n += 2
+        for i in range(L - 1, 0, -1):
+            src, K = (self.h[i - 2], H) if i > 1 else (self.x16, 784)
+            # dW_i[in,H] = src^T (MN-major) * dh_i (MN-major), K = batch
+            G.gemm_bf16_raw(src, self.dh[i - 1], g["fc%d_weights" % i], K, H, B, K, H, H, True, True,
+                            G.EPI_STORE_F32, bn=128)
+            n += 1
+            if i > 1:
+                # dh_{i-1} = (dh_i @ W_i^T) * relu'(h_{i-1});  W_i [in,out]: rows = in (N), K = out contiguous
+                G.gemm_bf16_raw(self.dh[i - 1], pb["fc%d_weights" % i], self.dh[i - 2], B, H, H, H, H, H, False, False,
+                                G.EPI_STORE_BF16, bn=128)
+                check(lib.dm_relu_bwd_colsum(ptr(self.dh[i - 2]), ptr(self.h[i - 2]), ptr(self.dh[i - 2]),
+                                             ptr(g["fc%d_biases" % (i - 1)]), B, H, sp), "relu_bwd_colsum")
+                n += 2
+        return n
+
+    def _launch_zero(self) -> int:
+        sp, base = stream_ptr(), self.grads.data_ptr()
+        for (a, b) in self._zero_ranges:
+            check(self.lib.dm_memset_async(ctypes.c_void_p(base + 4 * a), 0, ctypes.c_ulonglong(4 * (b - a)), sp), "memset")
+        check(self.lib.dm_memset_async(ptr(self.d_loss_acc), 0, ctypes.c_ulonglong(8), sp), "memset")
+        return 0
+
+    def _launch_step(self, slot: int, with_sync: bool) -> None:
+        B = self.batch_size
+        n = self._launch_zero()
+        n += self._forward(self.images[slot], self.labels[slot], B, True)
+        n += self._backward(B)
+        if with_sync:
+            if self._straggler is not None:
+                self.backend.enqueue_straggler_delay(self._straggler.prob, self._straggler.usec)
+                n += 1
+            self.backend.enqueue(self.params, self.grads, **self._opt_args)
+            n += 1
+        self.launches_per_step = n
+
+    @torch.no_grad()
+    def evaluate(self, images, labels) -> Tuple[float, float]:
+        if isinstance(images, np.ndarray):
+            images, labels = torch.from_numpy(np.ascontiguousarray(images)), torch.from_numpy(np.ascontiguousarray(labels))
+        images = images.reshape(-1, 784).to(self.device, torch.float32)
+        labels = labels.to(self.device, torch.int64)
+        n, B = images.shape[0], self.batch_size
+        tot_loss = tot_hit = 0.0
+        for s in range(0, n, B):
+            m = min(B, n - s)
+            self.d_loss_acc.zero_()
+            self._forward(images[s:s + m].contiguous(), labels[s:s + m].contiguous(), m, False)
+            la = self.d_loss_acc.cpu()
+            tot_loss += float(la[0]) * m
+            tot_hit += float(la[1]) * m
+        return tot_loss / n, tot_hit / n
+
+
 def make_cuda_engine(flags, ctx, backend) -> ComputeEngine:
     if not isinstance(backend, FusedBackend):
         raise RuntimeError("the sm_100a engine needs the fused backend")
     if flags.model == "lenet":
         return CudaLeNetEngine(flags.batch_size, backend, seed=flags.seed, rank=ctx.rank,
                                keep_prob=flags.dropout_keep_prob, use_graph=flags.use_cuda_graph)
-    # MLP families: tcgen05 GEMM engine is not wired yet; torch compute feeding the fused aggregation kernel.
-    return TorchEngine(flags.model, flags.batch_size, ctx.device, backend.allocate, seed=flags.seed, rank=ctx.rank,
-                       keep_prob=flags.dropout_keep_prob, mlp_hidden=flags.mlp_hidden,
-                       autocast_bf16=(flags.compute_dtype == "bf16"))
+    return CudaMlpEngine(flags.model, flags.batch_size, backend, hidden=flags.mlp_hidden, seed=flags.seed,
+                         rank=ctx.rank, use_graph=flags.use_cuda_graph)
 
 
 def make_cuda_eval_engine(flags, device: torch.device) -> ComputeEngine:
@@ -351,4 +496,4 @@ def make_cuda_eval_engine(flags, device: torch.device) -> ComputeEngine:
     backend = FusedBackend(ctx)
     if flags.model == "lenet":
         return CudaLeNetEngine(1000, backend, seed=flags.seed, keep_prob=flags.dropout_keep_prob, use_graph=False)
-    return TorchEngine(flags.model, 1, device, backend.allocate, seed=flags.seed, mlp_hidden=flags.mlp_hidden)
+    return CudaMlpEngine(flags.model, 1000, backend, hidden=flags.mlp_hidden, seed=flags.seed, use_graph=False)

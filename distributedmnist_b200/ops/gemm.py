@@ -13,14 +13,15 @@ import torch
 
 from .lib import check, load, ptr, stream_ptr
 
-EPI_STORE_F32, EPI_ATOMIC_F32, EPI_STORE_BF16 = 0, 1, 2
+EPI_STORE_F32, EPI_ATOMIC_F32, EPI_STORE_BF16, EPI_BIAS_RELU_BF16 = 0, 1, 2, 3
 
 
 def gemm_bf16_raw(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, M: int, N: int, K: int, lda: int, ldb: int,
                   ldo: int, a_mn: bool, b_mn: bool, epi: int, splits: int = 1, bn: int = 128,
-                  split_stride: int = 0, stream: Optional[torch.cuda.Stream] = None) -> None:
+                  split_stride: int = 0, bias: Optional[torch.Tensor] = None,
+                  stream: Optional[torch.cuda.Stream] = None) -> None:
     rc = load().dm_gemm_bf16(ptr(a), ptr(b), ptr(out), M, N, K, lda, ldb, ldo, int(a_mn), int(b_mn), epi, splits, bn,
-                             ctypes.c_longlong(split_stride), stream_ptr(stream))
+                             ctypes.c_longlong(split_stride), ptr(bias), stream_ptr(stream))
     check(rc, "dm_gemm_bf16")
 
 

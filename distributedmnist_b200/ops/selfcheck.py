@@ -44,7 +44,9 @@ def check_conv1_fwd(B: int = 8, seed: int = 0) -> List[Result]:
     b = (torch.randn(32, generator=g) * 0.1).to(dev)
     out = torch.zeros(B, 14, 14, 32, dtype=torch.bfloat16, device=dev)
     code = torch.zeros(B, 14, 14, 32, dtype=torch.uint8, device=dev)
-    check(lib.dm_conv1_fwd(ptr(x), ptr(w), ptr(b), ptr(out), ptr(code), B, stream_ptr()), "conv1_fwd")
+    junk = torch.ones(100, device=dev)
+    check(lib.dm_conv1_fwd(ptr(x), ptr(w), ptr(b), ptr(out), ptr(code), B, ptr(junk), 100, ctypes.c_void_p(0), 0,
+                           ctypes.c_void_p(0), 0, stream_ptr()), "conv1_fwd")
     conv = F.conv2d(x[:, None], w.permute(3, 2, 0, 1), b, padding=2)
     ref = _nhwc(F.max_pool2d(F.relu(conv), 2, 2))
     err = (out.float() - ref).abs().max().item()
@@ -54,7 +56,8 @@ def check_conv1_fwd(B: int = 8, seed: int = 0) -> List[Result]:
     sel = torch.gather(win, 4, idx[..., None])[..., 0]
     err_idx = (sel - win.max(dim=4).values).abs().max().item()
     err_act = ((sel > 0) != act).float().sum().item()
-    return [("conv1_fwd.out", err, 0.02), ("conv1_fwd.argmax", err_idx, 1e-5), ("conv1_fwd.relu_flag", err_act, 0.5)]
+    return [("conv1_fwd.out", err, 0.02), ("conv1_fwd.argmax", err_idx, 1e-5), ("conv1_fwd.relu_flag", err_act, 0.5),
+            ("conv1_fwd.zeroing", junk.abs().max().item(), 1e-12)]
 
 
 def check_conv2_fwd(B: int = 8, seed: int = 1) -> List[Result]:
@@ -192,5 +195,38 @@ def check_training_reduces_loss(B: int = 128, steps: int = 40) -> List[Result]:
             ("train.nan", float(any(l != l for l in losses)), 0.5)]
 
 
+def check_mlp_end_to_end(model: str = "mlp3", B: int = 256, hidden: int = 256, seed: int = 21) -> List[Result]:
+    """CudaMlpEngine forward+backward vs torch autograd on the bf16-emulating reference."""
+    from ..engine_cuda import CudaMlpEngine
+    from ..models import mlp_forward
+    ctx = ReplicaContext(0, 1, 0, torch.device("cuda", 0), "none")
+    eng = CudaMlpEngine(model, B, FusedBackend(ctx), hidden=hidden, seed=seed, use_graph=False)
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = (torch.rand(B, 28, 28, 1, generator=g) - 0.5)
+    y = torch.randint(0, 10, (B,), generator=g)
+    eng.load_batch(x.numpy(), y.numpy())
+    eng.forward_backward(0)
+    torch.cuda.synchronize()
+    loss, acc = eng.loss_acc()
+    flat = eng.params.detach().clone().requires_grad_(True)
+    logits = mlp_forward(eng.spec.views(flat), x.cuda(), emulate_bf16=True)
+    rloss, racc = loss_and_accuracy(logits, y.cuda())
+    rloss.backward()
+    out: List[Result] = [("%s.loss" % model, abs(loss - rloss.item()), 0.02 * max(1.0, abs(rloss.item()))),
+                         ("%s.acc" % model, abs(acc - racc.item()), 2.0 / B + 1e-6)]
+    gv, rv = eng.spec.views(eng.grads), eng.spec.views(flat.grad)
+    for name in rv:
+        scale = rv[name].abs().max().item() + 1e-8
+        out.append(("%s.grad.%s(rel)" % (model, name), (gv[name] - rv[name]).abs().max().item() / scale, 0.06))
+    out.append(("%s.grad.padding" % model, eng.grads[~eng.spec.valid_mask().cuda()].abs().max().item(), 1e-12))
+    el, ea = eng.evaluate(x.numpy(), y.numpy())
+    out.append(("%s.eval_loss" % model, abs(el - rloss.item()), 0.02 * max(1.0, abs(rloss.item()))))
+    return out
+
+
+def check_mlp2_end_to_end() -> List[Result]:
+    return check_mlp_end_to_end("mlp2", B=96, hidden=128, seed=22)
+
+
 ALL_CHECKS = [check_conv1_fwd, check_conv2_fwd, check_conv2_dgrad, check_conv2_wgrad, check_fc2_loss,
-              check_end_to_end, check_training_reduces_loss]
+              check_end_to_end, check_training_reduces_loss, check_mlp_end_to_end, check_mlp2_end_to_end]

@@ -43,3 +43,8 @@ def test_end_to_end_gradients_match_autograd():
 
 def test_training_under_cuda_graph_reduces_loss():
     _run("check_training_reduces_loss")
+
+
+def test_mlp_engines_match_autograd():
+    _run("check_mlp_end_to_end")                       # 3-layer, batch 256
+    _run("check_mlp2_end_to_end")                      # 2-layer, batch 96 (partial tiles everywhere)
