@@ -43,11 +43,25 @@ DMNIST_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// 16-byte vector reduction into global memory (sm_90+): one instruction adds four consecutive floats.
+DMNIST_DEVICE void red_add_f32x4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 DMNIST_DEVICE uint64_t globaltimer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+
+// ---------------------------------------------------------------------------------
+// programmatic dependent launch
+// ---------------------------------------------------------------------------------
+// Block until every kernel this launch depends on has completed and its writes are visible
+// (no-op when the kernel was launched without the PDL attribute).
+DMNIST_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Allow the dependent kernel's CTAs to be scheduled (they still block in their own pdl_wait()).
+DMNIST_DEVICE void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------
 // mbarrier

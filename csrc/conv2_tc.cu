@@ -25,8 +25,8 @@ constexpr int W_BYTES = 800 * 64 * 2;   // 102400
 // ------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------
-constexpr int FW_STAGES = 6;
-constexpr int FW_A_BYTES = 12 * 16 * 32 * 2;   // one kw-patch: 12 rows x 16 pixels x 32 ch = 12 KB (5 kh taps inside)
+constexpr int FW_STAGES = 4;
+constexpr int FW_A_BYTES = 20 * 12 * 32 * 2;   // ONE patch per tile: 20 rows x 12 pixels x 32 ch = 15 KB, all 25 taps inside
 struct FwSmem {
   static constexpr int A_OFF = W_BYTES;
   static constexpr int BAR_OFF = A_OFF + FW_STAGES * FW_A_BYTES;
@@ -34,7 +34,7 @@ struct FwSmem {
 };
 
 __global__ void __launch_bounds__(CV_THREADS, 1)
-conv2_fwd_kernel(const __grid_constant__ CUtensorMap tmX,   // a1 NHWC [B,14,14,32], box (32,16,12,1), 64B swizzle
+conv2_fwd_kernel(const __grid_constant__ CUtensorMap tmX,   // a1 NHWC [B,14,14,32], box (32,12,20,1), 64B swizzle
                  const __grid_constant__ CUtensorMap tmW,   // W [800][64], box (64,200), 128B swizzle
                  const float* __restrict__ bias,            // [64]
                  __nv_bfloat16* __restrict__ out,           // pooled [B,7,7,64]
@@ -63,22 +63,22 @@ conv2_fwd_kernel(const __grid_constant__ CUtensorMap tmX,   // a1 NHWC [B,14,14,
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();
+  // (no early launch_dependents: resident-but-blocked CTAs of the next kernel steal SM resources from this one)
 
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(w_full, W_BYTES);
       for (int i = 0; i < 4; ++i) tma_load_2d(smem + i * 25600, &tmW, w_full, 0, 200 * i);
       int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int img = t >> 1, h0 = (t & 1) * 8;
-        for (int kw = 0; kw < 5; ++kw, ++it) {
-          // one patch per horizontal tap offset: rows h0-2 .. h0+9; the five vertical taps are row offsets
-          // inside it (16 pixels = 1024 B, a multiple of the 512 B swizzle period)
-          const int s = it % FW_STAGES;
-          mbar_wait(&a_empty[s], ((it / FW_STAGES) & 1) ^ 1);
-          mbar_expect_tx(&a_full[s], FW_A_BYTES);
-          tma_load_4d(smem + FwSmem::A_OFF + s * FW_A_BYTES, &tmX, &a_full[s], 0, kw - 2, h0 - 2, img);
-        }
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        // tile = 16 rows x 8 columns of one image (columns w0 .. w0+7); its receptive field is the 20 x 12 patch
+        // starting at (-2, w0-2).  One TMA box; halo, rows 14-15 and columns 14-15 are OOB zero fill.
+        const int img = t >> 1, w0 = (t & 1) * 8;
+        const int s = it % FW_STAGES;
+        mbar_wait(&a_empty[s], ((it / FW_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&a_full[s], FW_A_BYTES);
+        tma_load_4d(smem + FwSmem::A_OFF + s * FW_A_BYTES, &tmX, &a_full[s], 0, w0 - 2, -2, img);
       }
     }
   } else if (warp == 1) {
@@ -89,26 +89,32 @@ conv2_fwd_kernel(const __grid_constant__ CUtensorMap tmX,   // a1 NHWC [B,14,14,
       const int buf = tl & 1;
       mbar_wait(&acc_empty[buf], ((tl >> 1) & 1) ^ 1);
       tc_fence_after_sync();
-      for (int kw = 0; kw < 5; ++kw, ++it) {
+      {
         const int s = it % FW_STAGES;
         mbar_wait(&a_full[s], (it / FW_STAGES) & 1);
         tc_fence_after_sync();
         if (elect_one()) {
-          const uint32_t a_addr = smem_u32(smem + FwSmem::A_OFF + s * FW_A_BYTES);
+          // output pixel (h, w) reads patch pixel (h + kh, w + kw): the window of tap (kh,kw) starts (kh*12 + kw)
+          // rows into the patch; 8-row groups (fixed h) are one patch row = 12 pixels = 768 B apart.  A descriptor
+          // may start at any row of the swizzled buffer (the hardware XORs absolute address bits:
+          // profiles/umma_row_shift_probe_r1.txt).  Descriptors = one base + compile-time offsets (>> 4).
+          const uint64_t da0 = make_smem_desc(smem_u32(smem + FwSmem::A_OFF + s * FW_A_BYTES), 16, 768, SWZ_64B);
+          const uint64_t db0 = make_smem_desc(smem_u32(smem), 8192, 1024, SWZ_128B);
+          const uint32_t tm = tmem_base + buf * 64;
 #pragma unroll
-          for (int kh = 0; kh < 5; ++kh) {
-            const uint32_t b_addr = smem_u32(smem + (kh * 5 + kw) * 4096);
+          for (int tap = 0; tap < 25; ++tap) {
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-              const uint64_t da = make_smem_desc(a_addr + kh * 1024 + 32 * k, 16, 512, SWZ_64B);  // 64 B rows, 8-row groups 512 B
-              const uint64_t db = make_smem_desc(b_addr + 2048 * k, 8192, 1024, SWZ_128B);      // 16 ci rows per step
-              umma_bf16(tmem_base + buf * 64, da, db, idesc, (kw | kh | k) != 0);
+              const uint64_t da = da0 + (uint64_t)((((tap / 5) * 12 + (tap % 5)) * 64 + 32 * k) >> 4);
+              const uint64_t db = db0 + (uint64_t)((tap * 4096 + 2048 * k) >> 4);     // 16 ci rows per step
+              umma_bf16(tm, da, db, idesc, (tap | k) != 0);
             }
           }
           umma_commit(&a_empty[s]);
-          if (kw == 4) umma_commit(&acc_full[buf]);
+          umma_commit(&acc_full[buf]);
         }
         __syncwarp();
+        ++it;
       }
     }
   } else {
@@ -116,13 +122,14 @@ conv2_fwd_kernel(const __grid_constant__ CUtensorMap tmX,   // a1 NHWC [B,14,14,
     int tl = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tl) {
       const int buf = tl & 1;
-      const int img = t >> 1, h0 = (t & 1) * 8;
+      const int img = t >> 1, w0 = (t & 1) * 8;
       mbar_wait(&acc_full[buf], (tl >> 1) & 1);
       tc_fence_after_sync();
-      const int w = lane & 15;
-      const int ph = (h0 >> 1) + q, pw = w >> 1;
-      const bool valid = (h0 + 2 * q < 14) && (w < 14);
-      const int qp = ((lane >> 4) << 1) | (lane & 1);   // position inside the 2x2 pooling window
+      // accumulator row = h*8 + w: this warp holds rows h = 4q .. 4q+3; lane = (h & 3) * 8 + w
+      const int w = w0 + (lane & 7), h = 4 * q + (lane >> 3);
+      const int ph = h >> 1, pw = w >> 1;
+      const bool valid = (h < 14) && (w < 14);
+      const int qp = (((lane >> 3) & 1) << 1) | (lane & 1);   // position inside the 2x2 pooling window
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
@@ -136,13 +143,13 @@ conv2_fwd_kernel(const __grid_constant__ CUtensorMap tmX,   // a1 NHWC [B,14,14,
           const float odd = (lane & 1) ? a : b, even = (lane & 1) ? b : a;
           bits0 |= (odd > even ? 1u : 0u) << j;           // argmax column inside my row pair
           const float m1 = fmaxf(a, b);
-          const float o = __shfl_xor_sync(0xffffffffu, m1, 16);
-          const float bot = (lane & 16) ? m1 : o, top = (lane & 16) ? o : m1;
+          const float o = __shfl_xor_sync(0xffffffffu, m1, 8);
+          const float bot = (lane & 8) ? m1 : o, top = (lane & 8) ? o : m1;
           bits1 |= (bot > top ? 1u : 0u) << j;            // argmax row
           v[j] = __float_as_uint(fmaxf(m1, o));
         }
-        const uint32_t other = __shfl_xor_sync(0xffffffffu, bits0, 16);
-        const uint32_t bits_top = (lane & 16) ? other : bits0, bits_bot = (lane & 16) ? bits0 : other;
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, bits0, 8);
+        const uint32_t bits_top = (lane & 8) ? other : bits0, bits_bot = (lane & 8) ? bits0 : other;
         if (valid) {
           // every lane of the 2x2 window now holds the pooled values of all 32 channels; each writes 8
           uint32_t pk[4];
@@ -185,8 +192,8 @@ conv2_fwd_kernel(const __grid_constant__ CUtensorMap tmX,   // a1 NHWC [B,14,14,
 // ------------------------------------------------------------------------------------------------------
 // dgrad
 // ------------------------------------------------------------------------------------------------------
-constexpr int DG_STAGES = 4;
-constexpr int DG_A_BYTES = 12 * 16 * 64 * 2;   // one kw-patch: 12 rows x 16 pixels x 64 ch = 24 KB
+constexpr int DG_STAGES = 3;
+constexpr int DG_A_BYTES = 20 * 12 * 64 * 2;   // ONE patch per tile: 20 rows x 12 pixels x 64 ch = 30 KB
 struct DgSmem {
   static constexpr int A_OFF = W_BYTES;
   static constexpr int BAR_OFF = A_OFF + DG_STAGES * DG_A_BYTES;
@@ -194,10 +201,10 @@ struct DgSmem {
 };
 
 __global__ void __launch_bounds__(CV_THREADS, 1)
-conv2_dgrad_kernel(const __grid_constant__ CUtensorMap tmDY,  // dY NHWC [B,14,14,64], box (64,16,12,1), 128B swizzle
+conv2_dgrad_kernel(const __grid_constant__ CUtensorMap tmDY,  // dY NHWC [B,14,14,64], box (64,12,20,1), 128B swizzle
                    const __grid_constant__ CUtensorMap tmW,
                    __nv_bfloat16* __restrict__ dx,            // [B,14,14,32]
-                   int num_tiles) {
+                   int num_tiles, unsigned long long* __restrict__ dbg) {   // dbg: optional timeline of CTA 0
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + DgSmem::BAR_OFF);
@@ -216,57 +223,66 @@ conv2_dgrad_kernel(const __grid_constant__ CUtensorMap tmDY,  // dY NHWC [B,14,1
     mbar_init(w_full, 1);
     fence_mbar_init();
   }
+  const bool dbg_on = dbg != nullptr && blockIdx.x == 0;
+  if (dbg_on && threadIdx.x == 0) dbg[0] = globaltimer_ns();
   if (warp == 1) tmem_alloc<64>(tmem_holder);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();
+  // (no early launch_dependents: resident-but-blocked CTAs of the next kernel steal SM resources from this one)
+  if (dbg_on && threadIdx.x == 0) dbg[1] = globaltimer_ns();
 
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(w_full, W_BYTES);
       for (int i = 0; i < 4; ++i) tma_load_2d(smem + i * 25600, &tmW, w_full, 0, 200 * i);
       int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int img = t >> 1, h0 = (t & 1) * 8;
-        for (int kw = 0; kw < 5; ++kw, ++it) {
-          const int s = it % DG_STAGES;
-          mbar_wait(&a_empty[s], ((it / DG_STAGES) & 1) ^ 1);
-          mbar_expect_tx(&a_full[s], DG_A_BYTES);
-          // dX[y,x] += dY[y - (kh-2), x - (kw-2)] * W[kh,kw]: patch rows h0-2 .. h0+9 at column offset 2-kw;
-          // tap kh starts at patch row 4-kh
-          tma_load_4d(smem + DgSmem::A_OFF + s * DG_A_BYTES, &tmDY, &a_full[s], 0, 2 - kw, h0 - 2, img);
-        }
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int img = t >> 1, w0 = (t & 1) * 8;
+        const int s = it % DG_STAGES;
+        mbar_wait(&a_empty[s], ((it / DG_STAGES) & 1) ^ 1);
+        if (dbg_on && it < 20) dbg[8 + it] = globaltimer_ns();          // producer: slot free, issuing load `it`
+        mbar_expect_tx(&a_full[s], DG_A_BYTES);
+        // dX[y,x] += dY[y + 2 - kh, x + 2 - kw] * W[kh,kw]: same 20 x 12 patch at (-2, w0-2); tap (kh,kw)
+        // starts (4-kh) rows and (4-kw) pixels into it
+        tma_load_4d(smem + DgSmem::A_OFF + s * DG_A_BYTES, &tmDY, &a_full[s], 0, w0 - 2, -2, img);
       }
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = make_idesc_bf16(128, 32, false, false);
     mbar_wait(w_full, 0);
+    if (dbg_on && lane == 0) dbg[2] = globaltimer_ns();                       // weights resident
     int it = 0, tl = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tl) {
       const int buf = tl & 1;
       mbar_wait(&acc_empty[buf], ((tl >> 1) & 1) ^ 1);
       tc_fence_after_sync();
-      for (int kw = 0; kw < 5; ++kw, ++it) {
+      {
         const int s = it % DG_STAGES;
         mbar_wait(&a_full[s], (it / DG_STAGES) & 1);
         tc_fence_after_sync();
+        if (dbg_on && lane == 0 && it < 20) dbg[32 + it] = globaltimer_ns();   // MMA: data of load `it` landed
         if (elect_one()) {
-          const uint32_t a_addr = smem_u32(smem + DgSmem::A_OFF + s * DG_A_BYTES);
+          // tap (kh,kw) starts (4-kh) patch rows and (4-kw) pixels into the patch; 128 B per pixel, groups 12*128 B apart
+          const uint64_t da0 = make_smem_desc(smem_u32(smem + DgSmem::A_OFF + s * DG_A_BYTES), 16, 1536, SWZ_128B);
+          const uint64_t db0 = make_smem_desc(smem_u32(smem), 16, 1024, SWZ_128B);   // W[tap]: 32 ci rows x 64 co, K-major
+          const uint32_t tm = tmem_base + buf * 32;
 #pragma unroll
-          for (int kh = 0; kh < 5; ++kh) {
-            const uint32_t b_addr = smem_u32(smem + (kh * 5 + kw) * 4096);   // W[tap]: 32 ci rows x 64 co (128 B), K-major
+          for (int tap = 0; tap < 25; ++tap) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint64_t da = make_smem_desc(a_addr + (4 - kh) * 2048 + 32 * k, 16, 1024, SWZ_128B);
-              const uint64_t db = make_smem_desc(b_addr + 32 * k, 16, 1024, SWZ_128B);
-              umma_bf16(tmem_base + buf * 32, da, db, idesc, (kw | kh | k) != 0);
+              const uint64_t da = da0 + (uint64_t)((((4 - tap / 5) * 12 + (4 - tap % 5)) * 128 + 32 * k) >> 4);
+              const uint64_t db = db0 + (uint64_t)((tap * 4096 + 32 * k) >> 4);
+              umma_bf16(tm, da, db, idesc, (tap | k) != 0);
             }
           }
           umma_commit(&a_empty[s]);
-          if (kw == 4) umma_commit(&acc_full[buf]);
+          umma_commit(&acc_full[buf]);
         }
         __syncwarp();
+        ++it;
       }
     }
   } else {
@@ -274,15 +290,16 @@ conv2_dgrad_kernel(const __grid_constant__ CUtensorMap tmDY,  // dY NHWC [B,14,1
     int tl = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tl) {
       const int buf = tl & 1;
-      const int img = t >> 1, h0 = (t & 1) * 8;
+      const int img = t >> 1, w0 = (t & 1) * 8;
       mbar_wait(&acc_full[buf], (tl >> 1) & 1);
       tc_fence_after_sync();
+      if (dbg_on && q == 0 && lane == 0 && tl < 8) dbg[56 + tl] = globaltimer_ns();   // epilogue: accumulator of tile tl complete
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 32, v);
       tmem_ld_wait();
       tc_fence_before_sync();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
-      const int h = h0 + 2 * q + (lane >> 4), w = lane & 15;
+      const int h = 4 * q + (lane >> 3), w = w0 + (lane & 7);
       if (h < 14 && w < 14) {
         __nv_bfloat16* o = dx + (((size_t)img * 14 + h) * 14 + w) * 32;
 #pragma unroll
@@ -297,25 +314,32 @@ conv2_dgrad_kernel(const __grid_constant__ CUtensorMap tmDY,  // dY NHWC [B,14,1
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (dbg_on && threadIdx.x == 0) dbg[3] = globaltimer_ns();
   if (warp == 1) tmem_dealloc<64>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------------
-// wgrad: CTA = (group of 4 taps, slice of the pixel tiles)
+// wgrad: CTA = (group of 4 taps, slice of the pixel tiles).  Per pixel tile (16 rows x 8 columns) a stage
+// holds the same 20 x 12 input patch as the forward pass (15 KB, A operand for every tap of the group) and
+// the 16 x 8 tile of dY (16 KB, B operand).  M = (tap, ci): the four taps of a group are M-chunks whose
+// windows start a uniform distance apart inside the patch:
+//     group g < 5 : taps (kh = 0..3, kw = g)   -> chunk stride = one patch row = 768 B
+//     group 5     : taps (kh = 4, kw = 0..3)   -> chunk stride = one pixel     =  64 B
+//     group 6     : tap  (kh = 4, kw = 4) + three padding chunks (computed, never stored)
 // ------------------------------------------------------------------------------------------------------
-constexpr int WG_STAGES = 4;
-constexpr int WG_A_BYTES = 4 * 128 * 32 * 2;   // 4 taps x 8 KB
-constexpr int WG_B_BYTES = 128 * 64 * 2;       // 16 KB
-constexpr int WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES;
-constexpr int WG_GROUPS = 7;                   // ceil(25 / 4)
+constexpr int WG_STAGES = 6;
+constexpr int WG_A_BYTES = 20 * 12 * 32 * 2;   // 15 KB patch
+constexpr int WG_B_BYTES = 128 * 64 * 2;       // 16 KB dY tile
+constexpr int WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES + 1024;   // keep the dY tile 1024-aligned (128B swizzle)
+constexpr int WG_GROUPS = 7;
 struct WgSmem {
   static constexpr int BAR_OFF = WG_STAGES * WG_STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024 + 4096;     // + slack: group 6's padding chunks read past the patch
 };
 
 __global__ void __launch_bounds__(CV_THREADS, 1)
-conv2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,    // a1, box (32,16,8,1), 64B swizzle
-                   const __grid_constant__ CUtensorMap tmDY,   // dY, box (64,16,8,1), 128B swizzle
+conv2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,    // a1, box (32,12,20,1), 64B swizzle
+                   const __grid_constant__ CUtensorMap tmDY,   // dY, box (64,8,16,1), 128B swizzle
                    float* __restrict__ g_w,                    // [25][32][64] fp32, accumulated atomically
                    int num_tiles, int splits) {
   extern __shared__ uint8_t smem_raw[];
@@ -329,6 +353,9 @@ conv2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,    // a1, box (32,16
   const int t_begin = (int)(((long long)num_tiles * split) / splits);
   const int t_end = (int)(((long long)num_tiles * (split + 1)) / splits);
   const int nt = t_end - t_begin;
+  // first tap of the group (as a pixel offset into the patch) and the byte distance between its four M-chunks
+  const int base_px = group < 5 ? group : (group == 5 ? 4 * 12 : 4 * 12 + 4);
+  const uint32_t lbo = group < 5 ? 768u : 64u;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -342,21 +369,19 @@ conv2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,    // a1, box (32,16
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();
+  // (no early launch_dependents: resident-but-blocked CTAs of the next kernel steal SM resources from this one)
 
   if (warp == 0) {
     if (lane == 0) {
       for (int i = 0; i < nt; ++i) {
-        const int t = t_begin + i, img = t >> 1, h0 = (t & 1) * 8;
+        const int t = t_begin + i, img = t >> 1, w0 = (t & 1) * 8;
         const int s = i % WG_STAGES;
         mbar_wait(&empty[s], ((i / WG_STAGES) & 1) ^ 1);
         uint8_t* sA = smem + s * WG_STAGE_BYTES;
-        mbar_expect_tx(&full[s], WG_STAGE_BYTES);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int tap = min(group * 4 + j, 24);   // the last group is padded with copies of tap 24
-          tma_load_4d(sA + j * 8192, &tmX, &full[s], 0, tap % 5 - 2, h0 + tap / 5 - 2, img);
-        }
-        tma_load_4d(sA + WG_A_BYTES, &tmDY, &full[s], 0, 0, h0, img);
+        mbar_expect_tx(&full[s], WG_A_BYTES + WG_B_BYTES);
+        tma_load_4d(sA, &tmX, &full[s], 0, w0 - 2, -2, img);
+        tma_load_4d(sA + WG_A_BYTES + 1024, &tmDY, &full[s], 0, w0, 0, img);
       }
     }
   } else if (warp == 1) {
@@ -366,26 +391,26 @@ conv2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,    // a1, box (32,16
       mbar_wait(&full[s], (i / WG_STAGES) & 1);
       tc_fence_after_sync();
       if (elect_one()) {
-        const uint32_t a_addr = smem_u32(smem + s * WG_STAGE_BYTES);
-        const uint32_t b_addr = a_addr + WG_A_BYTES;
+        const uint32_t a_addr = smem_u32(smem + s * WG_STAGE_BYTES) + base_px * 64;
+        const uint32_t b_addr = smem_u32(smem + s * WG_STAGE_BYTES) + WG_A_BYTES + 1024;
+        // A (MN-major, 64B swizzle): k = pixel; 8-pixel groups (one tile row) are one patch row = 768 B apart,
+        //   M-chunks (taps) `lbo` apart; a K step = 16 pixels = two tile rows = 1536 B.
+        // B (MN-major, 128B swizzle): [pixel][64 co], 8-pixel groups 1024 B apart; K step = 2048 B.
+        const uint64_t da0 = make_smem_desc(a_addr, lbo, 768, SWZ_64B);
+        const uint64_t db0 = make_smem_desc(b_addr, 8192, 1024, SWZ_128B);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {   // 16 pixels per step
-          // A: [pixel][32 ci] per tap, 64 B rows; 8-pixel groups 512 B apart; the 4 taps (M chunks) 8192 B apart
-          const uint64_t da = make_smem_desc(a_addr + 1024 * k, 8192, 512, SWZ_64B);
-          // B: [pixel][64 co], 128 B rows; 8-pixel groups 1024 B apart
-          const uint64_t db = make_smem_desc(b_addr + 2048 * k, 8192, 1024, SWZ_128B);
-          umma_bf16(tmem_base, da, db, idesc, (i | k) != 0);
-        }
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem_base, da0 + (uint64_t)((1536 * k) >> 4), db0 + (uint64_t)((2048 * k) >> 4), idesc, (i | k) != 0);
         umma_commit(&empty[s]);
         if (i == nt - 1) umma_commit(acc_full);
       }
       __syncwarp();
     }
   } else if (nt > 0) {
-    const int q = warp & 3;
+    const int q = warp & 3;               // rows 32q .. 32q+31 = M-chunk q of the group, row = ci
     mbar_wait(acc_full, 0);
     tc_fence_after_sync();
-    const int tap = group * 4 + q;        // rows 32q .. 32q+31 belong to tap q of the group, row = ci
+    const int tap = group < 5 ? q * 5 + group : (group == 5 ? 20 + q : (q == 0 ? 24 : 25));
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       uint32_t v[32];
@@ -394,7 +419,9 @@ conv2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,    // a1, box (32,16
       if (tap < 25) {
         float* o = g_w + ((size_t)tap * 32 + lane) * 64 + c * 32;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(o + j, __uint_as_float(v[j]));
+        for (int j = 0; j < 32; j += 4)
+          red_add_f32x4(o + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                        __uint_as_float(v[j + 3]));
       }
     }
   }
@@ -411,7 +438,7 @@ extern "C" {
 int dm_conv2_fwd(const void* a1, const void* w_bf16, const void* bias, void* out, void* code, int B, void* stream) {
   using namespace dm;
   CUtensorMap tmX, tmW;
-  if (make_tmap_nhwc_bf16(&tmX, a1, 32, 14, 14, B, 32, 16, 12, 64)) return 101;
+  if (make_tmap_nhwc_bf16(&tmX, a1, 32, 14, 14, B, 32, 12, 20, 64)) return 101;
   if (make_tmap_2d_bf16(&tmW, w_bf16, 64, 800, 64, 64, 200, 128)) return 102;
   static bool configured = false;
   if (!configured) {
@@ -420,17 +447,20 @@ int dm_conv2_fwd(const void* a1, const void* w_bf16, const void* bias, void* out
   }
   const int tiles = 2 * B;
   const int grid = tiles < 148 ? tiles : 148;
-  conv2_fwd_kernel<<<grid, CV_THREADS, FwSmem::TOTAL, reinterpret_cast<cudaStream_t>(stream)>>>(
-      tmX, tmW, reinterpret_cast<const float*>(bias), reinterpret_cast<__nv_bfloat16*>(out),
-      reinterpret_cast<uint8_t*>(code), tiles);
-  return (int)cudaGetLastError();
+  return (int)launch_kernel(conv2_fwd_kernel, dim3(grid), dim3(CV_THREADS), FwSmem::TOTAL,
+                            reinterpret_cast<cudaStream_t>(stream), tmX, tmW, reinterpret_cast<const float*>(bias),
+                            reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<uint8_t*>(code), tiles);
 }
 
 // dy: [B,14,14,64] bf16 -> dx: [B,14,14,32] bf16
+int dm_conv2_dgrad_dbg(const void* dy, const void* w_bf16, void* dx, int B, void* dbg, void* stream);
 int dm_conv2_dgrad(const void* dy, const void* w_bf16, void* dx, int B, void* stream) {
+  return dm_conv2_dgrad_dbg(dy, w_bf16, dx, B, nullptr, stream);
+}
+int dm_conv2_dgrad_dbg(const void* dy, const void* w_bf16, void* dx, int B, void* dbg, void* stream) {
   using namespace dm;
   CUtensorMap tmDY, tmW;
-  if (make_tmap_nhwc_bf16(&tmDY, dy, 64, 14, 14, B, 64, 16, 12, 128)) return 101;
+  if (make_tmap_nhwc_bf16(&tmDY, dy, 64, 14, 14, B, 64, 12, 20, 128)) return 101;
   if (make_tmap_2d_bf16(&tmW, w_bf16, 64, 800, 64, 64, 200, 128)) return 102;
   static bool configured = false;
   if (!configured) {
@@ -439,17 +469,17 @@ int dm_conv2_dgrad(const void* dy, const void* w_bf16, void* dx, int B, void* st
   }
   const int tiles = 2 * B;
   const int grid = tiles < 148 ? tiles : 148;
-  conv2_dgrad_kernel<<<grid, CV_THREADS, DgSmem::TOTAL, reinterpret_cast<cudaStream_t>(stream)>>>(
-      tmDY, tmW, reinterpret_cast<__nv_bfloat16*>(dx), tiles);
-  return (int)cudaGetLastError();
+  return (int)launch_kernel(conv2_dgrad_kernel, dim3(grid), dim3(CV_THREADS), DgSmem::TOTAL,
+                            reinterpret_cast<cudaStream_t>(stream), tmDY, tmW, reinterpret_cast<__nv_bfloat16*>(dx), tiles,
+                            reinterpret_cast<unsigned long long*>(dbg));
 }
 
 // g_w ([25][32][64] fp32) must be zeroed by the caller; accumulated with atomics.
 int dm_conv2_wgrad(const void* a1, const void* dy, void* g_w, int B, void* stream) {
   using namespace dm;
   CUtensorMap tmX, tmDY;
-  if (make_tmap_nhwc_bf16(&tmX, a1, 32, 14, 14, B, 32, 16, 8, 64)) return 101;
-  if (make_tmap_nhwc_bf16(&tmDY, dy, 64, 14, 14, B, 64, 16, 8, 128)) return 102;
+  if (make_tmap_nhwc_bf16(&tmX, a1, 32, 14, 14, B, 32, 12, 20, 64)) return 101;
+  if (make_tmap_nhwc_bf16(&tmDY, dy, 64, 14, 14, B, 64, 8, 16, 128)) return 102;
   static bool configured = false;
   if (!configured) {
     DM_CUDA_OK(cudaFuncSetAttribute(conv2_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem::TOTAL));
@@ -458,9 +488,8 @@ int dm_conv2_wgrad(const void* a1, const void* dy, void* g_w, int B, void* strea
   const int tiles = 2 * B;
   int splits = 148 / WG_GROUPS;   // 21 -> 147 CTAs
   if (splits > tiles) splits = tiles;
-  conv2_wgrad_kernel<<<WG_GROUPS * splits, CV_THREADS, WgSmem::TOTAL, reinterpret_cast<cudaStream_t>(stream)>>>(
-      tmX, tmDY, reinterpret_cast<float*>(g_w), tiles, splits);
-  return (int)cudaGetLastError();
+  return (int)launch_kernel(conv2_wgrad_kernel, dim3(WG_GROUPS * splits), dim3(CV_THREADS), WgSmem::TOTAL,
+                            reinterpret_cast<cudaStream_t>(stream), tmX, tmDY, reinterpret_cast<float*>(g_w), tiles, splits);
 }
 
 }  // extern "C"

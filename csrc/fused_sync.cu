@@ -216,6 +216,7 @@ template <bool KOFN>
 __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_sgd_kernel(SyncPeers P, SyncArgs a) {
   SyncCtrl* me = P.ctrl[a.rank];
   __shared__ uint32_t s_mask, s_late, s_target, s_last;
+  pdl_wait();      // the gradient arena is complete only when the backward kernels have finished
   const uint32_t epoch = me->epoch;   // stable for the whole launch (only the last CTA writes it, at exit)
 
   const bool solo = a.nranks == 1;     // single replica: no arrival / commit / done protocol at all
@@ -416,9 +417,8 @@ int dm_fused_sync_sgd(void* const* ctrl, void* const* params, void* const* grads
   a.shadow = reinterpret_cast<__nv_bfloat16*>(shadow_bf16);
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (ctas < 1) ctas = 64;
-  if (k < nranks) fused_sync_sgd_kernel<true><<<ctas, SYNC_THREADS, 0, stream>>>(P, a);
-  else            fused_sync_sgd_kernel<false><<<ctas, SYNC_THREADS, 0, stream>>>(P, a);
-  return (int)cudaGetLastError();
+  if (k < nranks) return (int)launch_kernel(fused_sync_sgd_kernel<true>, dim3(ctas), dim3(SYNC_THREADS), 0, stream, P, a);
+  return (int)launch_kernel(fused_sync_sgd_kernel<false>, dim3(ctas), dim3(SYNC_THREADS), 0, stream, P, a);
 }
 
 int dm_f32_to_bf16(const void* src, void* dst, long long numel, void* stream_) {

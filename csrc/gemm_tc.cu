@@ -78,6 +78,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();      // everything above is private set-up; operands / outputs belong to earlier kernels until here
+  // (no early launch_dependents: resident-but-blocked CTAs of the next kernel steal SM resources from this one)
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -166,9 +168,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         } else if (EPI == EPI_ATOMIC_F32) {
           float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
+          if (col0 + 32 <= p.N && (p.ldo & 3) == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) atomicAdd(o + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; j += 4)
+              red_add_f32x4(o + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                            __uint_as_float(v[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) atomicAdd(o + j, __uint_as_float(v[j]));
+          }
         } else {
           if (EPI == EPI_BIAS_RELU_BF16) {
 #pragma unroll
@@ -216,8 +225,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     configured = true;
   }
   dim3 grid((p.M + GEMM_BM - 1) / GEMM_BM, (p.N + BN - 1) / BN, splits);
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(tmA, tmB, p);
-  return (int)cudaGetLastError();
+  return (int)launch_kernel(kern, grid, dim3(GEMM_THREADS), smem, stream, tmA, tmB, p);
 }
 
 template <int BN, int EPI>

@@ -4,6 +4,8 @@
 
 namespace dm {
 
+int g_pdl = 0;
+
 void* driver_symbol(const char* name) {
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -77,7 +79,12 @@ int make_tmap_nhwc_bf16(CUtensorMap* out, const void* base, int C, int W, int H,
 
 }  // namespace dm
 
-extern "C" int dm_version() { return 1; }
+extern "C" int dm_version() { return 2; }
+
+extern "C" int dm_set_pdl(int on) {
+  dm::g_pdl = on ? 1 : 0;
+  return dm::g_pdl;
+}
 
 // Device query used by the Python side to fail loudly on non-Blackwell parts.
 extern "C" int dm_device_cc(int device) {

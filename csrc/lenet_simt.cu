@@ -33,6 +33,8 @@ __global__ void __launch_bounds__(C1_THREADS) conv1_fwd_kernel(const float* __re
                                                                __nv_bfloat16* __restrict__ out,   // [B,14,14,32]
                                                                uint8_t* __restrict__ code,        // [B,14,14,32]
                                                                ZeroRanges zr) {
+  pdl_wait();
+  // (no early launch_dependents: resident-but-blocked CTAs of the next kernel steal SM resources from this one)
   // First kernel of a training step: also clears the gradient regions that later kernels accumulate into
   // with atomics and the loss accumulator (replaces three memset nodes of the step graph).
   {
@@ -152,6 +154,8 @@ struct Fc2Args {
 __global__ void __launch_bounds__(FC2_ROWS * 32) fc2_loss_kernel(Fc2Args a) {
   __shared__ float s_h[FC2_ROWS][HID];       // post ReLU/dropout activations (0 where killed)
   __shared__ float s_dl[FC2_ROWS][NCLS + 2];
+  pdl_wait();
+  // (no early launch_dependents: resident-but-blocked CTAs of the next kernel steal SM resources from this one)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t step = a.step_ptr ? *a.step_ptr : 0u;
   const uint32_t mix = a.seed_mix + step * 0x9E3779B9u;
@@ -271,6 +275,8 @@ __global__ void __launch_bounds__(256) unpool2_kernel(const __nv_bfloat16* __res
   __shared__ float s_gb[64];
   if (threadIdx.x < 64) s_gb[threadIdx.x] = 0.f;
   __syncthreads();
+  pdl_wait();
+  // (no early launch_dependents: resident-but-blocked CTAs of the next kernel steal SM resources from this one)
   const int total = B * 49 * 8;   // (b, pooled position, group of 8 channels)
   float gsum[8];                  // bias-gradient partials: a thread keeps the same channel group across trips
 #pragma unroll
@@ -333,6 +339,8 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restric
   __shared__ __align__(16) float s_g[8 * 26 * 32];     // [196][32] masked gradients; reused as [8][26][32] for the reduction
   __shared__ __align__(8) uint8_t s_pos[196 * 32];     // argmax position code (bits 0-1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_wait();
+  // (no early launch_dependents: resident-but-blocked CTAs of the next kernel steal SM resources from this one)
   float acc[26];
 #pragma unroll
   for (int t = 0; t < 26; ++t) acc[t] = 0.f;
@@ -386,6 +394,8 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restric
 // accumulator for the next split-K pass.  Backward companion: mask the incoming gradient.
 __global__ void bias_relu_bf16_kernel(float* __restrict__ acc, const float* __restrict__ bias,
                                       __nv_bfloat16* __restrict__ out, int rows, int cols, int zero_acc) {
+  pdl_wait();
+  // (no early launch_dependents: resident-but-blocked CTAs of the next kernel steal SM resources from this one)
   const long long n = (long long)rows * cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = acc[i] + bias[i % cols];
@@ -405,10 +415,9 @@ int dm_conv1_fwd(const void* images, const void* w, const void* bias, void* out,
   zr.ptr[0] = reinterpret_cast<float*>(zero0); zr.n[0] = n0;
   zr.ptr[1] = reinterpret_cast<float*>(zero1); zr.n[1] = n1;
   zr.ptr[2] = reinterpret_cast<float*>(zero2); zr.n[2] = n2;
-  dm::conv1_fwd_kernel<<<7 * B, dm::C1_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  return (int)dm::launch_kernel(dm::conv1_fwd_kernel, dim3(7 * B), dim3(dm::C1_THREADS), 0, reinterpret_cast<cudaStream_t>(stream),
       reinterpret_cast<const float*>(images), reinterpret_cast<const float*>(w), reinterpret_cast<const float*>(bias),
       reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<uint8_t*>(code), zr);
-  return (int)cudaGetLastError();
 }
 
 int dm_fc2_loss(const void* h_part, long long part_stride, int splits, const void* b1, const void* w2, const void* b2,
@@ -433,25 +442,23 @@ int dm_fc2_loss(const void* h_part, long long part_stride, int splits, const voi
   a.keep_prob = keep_prob;
   a.inv_batch = 1.f / (float)B;
   const int grid = (B + dm::FC2_ROWS - 1) / dm::FC2_ROWS;
-  dm::fc2_loss_kernel<<<grid, dm::FC2_ROWS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
-  return (int)cudaGetLastError();
+  return (int)dm::launch_kernel(dm::fc2_loss_kernel, dim3(grid), dim3(dm::FC2_ROWS * 32), 0,
+                                reinterpret_cast<cudaStream_t>(stream), a);
 }
 
 int dm_unpool2(const void* dpool, const void* code, void* dy, void* g_bias, int B, void* stream) {
   int grid = (B * 49 * 8 + 255) / 256;
   if (grid > 148 * 2) grid = 148 * 2;
-  dm::unpool2_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  return (int)dm::launch_kernel(dm::unpool2_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
       reinterpret_cast<const __nv_bfloat16*>(dpool), reinterpret_cast<const uint8_t*>(code),
       reinterpret_cast<__nv_bfloat16*>(dy), reinterpret_cast<float*>(g_bias), B);
-  return (int)cudaGetLastError();
 }
 
 int dm_conv1_wgrad(const void* images, const void* dpool, const void* code, void* g_w, void* g_b, int B, void* stream) {
   int grid = B < 148 ? B : 148;
-  dm::conv1_wgrad_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  return (int)dm::launch_kernel(dm::conv1_wgrad_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
       reinterpret_cast<const float*>(images), reinterpret_cast<const __nv_bfloat16*>(dpool),
       reinterpret_cast<const uint8_t*>(code), reinterpret_cast<float*>(g_w), reinterpret_cast<float*>(g_b), B);
-  return (int)cudaGetLastError();
 }
 
 int dm_bias_relu_bf16(void* acc, const void* bias, void* out, int rows, int cols, int zero_acc, void* stream) {

@@ -18,6 +18,7 @@ Two ways to drive it:
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -37,7 +38,8 @@ class FusedBackend(Backend):
         self.lib = load()
         require_blackwell(ctx.device)
         check(self.lib.dm_set_device(ctx.device.index or 0), "dm_set_device")
-        import os
+        # programmatic dependent launch between the kernels of a step (DMNIST_PDL=0 disables)
+        self.lib.dm_set_pdl(0 if os.environ.get("DMNIST_PDL", "1") == "0" else 1)
         self.ctas = ctas or int(os.environ.get("DMNIST_SYNC_CTAS", "148"))
         self.timeout_ms = timeout_ms
         self._buffers: List[SymmetricBuffer] = []

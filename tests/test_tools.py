@@ -2,6 +2,7 @@
 (reference tools/tf_ec2.py:17-25,445-615 and tools/benchmark.py)."""
 import os
 import struct
+import subprocess
 import sys
 
 import pytest
@@ -73,3 +74,9 @@ def test_end_to_end_cpu_experiment(tmp_path):
     assert len(t) >= 1 and 0.0 <= p[-1] <= 1.0, evaluator[-2000:]
     assert all(os.path.getsize(f) > 500 for f in figs)
     assert os.path.exists(tmp_path / "runs" / "2_workers_gloo_mlp2" / "results.txt")
+
+
+def test_ps_role_exits_cleanly():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "src", "mnist_distributed_train.py"), "--job_name=ps",
+                        "--task_id=0"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "no parameter server" in (r.stdout + r.stderr)
