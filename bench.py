@@ -42,6 +42,9 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_ddp"])
     ap.add_argument("--batch", type=int, default=256, help="per-replica batch (BASELINE.json: 256)")
     ap.add_argument("--k", type=int, default=-1, help="replicas_to_aggregate (-1 = all)")
+    ap.add_argument("--model", default="lenet", choices=["lenet", "mlp2", "mlp3"],
+                    help="lenet = the headline config; mlp3 at --batch 8192 = BASELINE.json large-message config")
+    ap.add_argument("--hidden", type=int, default=4096, help="MLP hidden width")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--straggler", default="", help="rank:prob:usec device-side delay injection")
     ap.add_argument("--kernel-times", action="store_true", help="also print per-kernel device times (stderr)")
@@ -130,7 +133,7 @@ def main():
         from baseline.torch_ddp import run_baseline
         return run_baseline(args)
 
-    from distributedmnist_b200.engine_cuda import CudaLeNetEngine
+    from distributedmnist_b200.engine_cuda import CudaLeNetEngine, CudaMlpEngine
     from distributedmnist_b200.parallel.aggregators import SyncReplicasOptimizer, parse_straggler_spec
     from distributedmnist_b200.parallel.fused import FusedBackend
     from distributedmnist_b200.schedule import LearningRateSchedule, decay_steps_for
@@ -142,7 +145,11 @@ def main():
     n, rank, B = ctx.world_size, ctx.rank, args.batch
     k = n if args.k < 0 else args.k
     backend = FusedBackend(ctx)
-    engine = CudaLeNetEngine(B, backend, seed=66478, rank=rank, use_graph=not args.no_graph)
+    if args.model == "lenet":
+        engine = CudaLeNetEngine(B, backend, seed=66478, rank=rank, use_graph=not args.no_graph)
+    else:
+        engine = CudaMlpEngine(args.model, B, backend, hidden=args.hidden, seed=66478, rank=rank,
+                               use_graph=not args.no_graph)
     sched = LearningRateSchedule(0.01, decay_steps_for(60000, B, 2.0, k), 0.999)
     opt = SyncReplicasOptimizer(backend, sched, replicas_to_aggregate=k, total_num_replicas=n,
                                 straggler=parse_straggler_spec(args.straggler))
@@ -151,11 +158,10 @@ def main():
     # ---- synthetic data ------------------------------------------------------------------------------------
     # host pool (pinned) for the e2e path; device pool > L2 (126 MB) for the device-timed path
     g = torch.Generator().manual_seed(1234 + rank)
-    pool_n = 208                                             # 208 x 256 x 784 x 4 B = 167 MB > 126 MB L2
-    if B * 784 * 4 * pool_n < 160e6:
-        pool_n = int(160e6 / (B * 784 * 4)) + 1
-    h_imgs = (torch.rand(32, B, 28, 28, generator=g) - 0.5).pin_memory()
-    h_lbls = torch.randint(0, 10, (32, B), generator=g).pin_memory()
+    pool_n = int(160e6 / (B * 784 * 4)) + 1
+    n_host = 32 if B <= 1024 else 4
+    h_imgs = (torch.rand(n_host, B, 28, 28, generator=g) - 0.5).pin_memory()
+    h_lbls = torch.randint(0, 10, (n_host, B), generator=g).pin_memory()
     d_imgs = (torch.rand(pool_n, B, 28, 28, device=ctx.device) - 0.5)
     d_lbls = torch.randint(0, 10, (pool_n, B), device=ctx.device)
 
@@ -168,14 +174,14 @@ def main():
     def device_step(i: int):
         # inputs come from the device pool (cold in L2); slot buffers are what the captured graph reads
         s = i & 1
-        engine.images[s].copy_(d_imgs[i % pool_n])
+        engine.images[s].copy_(d_imgs[i % pool_n].view(engine.images[s].shape))
         engine.labels[s].copy_(d_lbls[i % pool_n])
         engine._slot = s
         engine._copy_done[s].record()
         engine.train_step()
 
     def e2e_step(i: int):
-        engine.load_batch(h_imgs[i % 32], h_lbls[i % 32])     # pinned host -> device (copy stream)
+        engine.load_batch(h_imgs[i % n_host], h_lbls[i % n_host])     # pinned host -> device (copy stream)
         engine.train_step()
         return engine.read_loss_async()                       # device -> host, read one step later
 
@@ -238,7 +244,8 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "impl": "ours",
-            "config": {"model": "LeNet-like MNIST convnet (1,663,370 params, reference src/mnist.py)",
+            "config": {"model": ("LeNet-like MNIST convnet (1,663,370 params, reference src/mnist.py)" if args.model == "lenet"
+                                 else "%s hidden=%d (%d params)" % (args.model, args.hidden, engine.spec.num_trainable)),
                        "global_batch": n * B, "batch_per_replica": B, "seq_len": None,
                        "parallelism": "dp%d (sync replicas, K=%d of %d, fused NVLink allreduce+SGD kernel)" % (n, k, n),
                        "optimizer": "SGD, staircase exp-decay LR evaluated on device",
@@ -251,6 +258,7 @@ def main():
                     "last_loss": last_loss},
             "gpu_launches": launches, "gpu_launches_per_step": engine.launches_per_step,
             "final_global_step": info.global_step,
+            "sync_phases_ns": dict(zip(["start", "decided", "reduced", "pushed", "landed", "end"], backend.read_phases())),
         }
         print(json.dumps(out))
     sys.stdout.flush()

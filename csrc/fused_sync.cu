@@ -260,50 +260,48 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_sgd_kernel(SyncPee
     for (int q = 0; q < a.nranks; ++q)
       if ((mask >> q) & 1u) contrib[nc++] = q;
     const float* wsrc = P.params[a.rank];
-    constexpr int U = 4;
+    // Latency is the enemy here (a remote load is ~2 us): every thread issues the loads of ALL contributors
+    // for U elements before it touches any of them, so one NVLink round trip covers the whole reduction of
+    // its elements (at N = 8 a shard is so small that most threads make exactly one trip).
+    constexpr int U = 2;
     const int stride = gridDim.x * SYNC_THREADS;
     for (int i0 = begin + blockIdx.x * SYNC_THREADS + threadIdx.x; i0 < end; i0 += U * stride) {
-      float4 acc[U], w[U];
+      float4 g[U][SYNC_MAX_RANKS], w[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         const int i = i0 + u * stride;
+#pragma unroll
+        for (int c = 0; c < SYNC_MAX_RANKS; ++c)
+          g[u][c] = (c < nc && i < end) ? ld_peer_f4(P.grads[contrib[c]] + 4 * (size_t)i) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < end) w[u] = *reinterpret_cast<const float4*>(wsrc + 4 * (size_t)i);
       }
-      for (int c = 0; c < nc; ++c) {
-        const int q = contrib[c];
-        float4 g[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {   // U remote loads in flight per contributor
-          const int i = i0 + u * stride;
-          g[u] = (i < end) ? ld_peer_f4(P.grads[q] + 4 * (size_t)i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (drop_thresh) {   // drop-connect: contributor q's Bernoulli mask, no 1/p rescale (reference :414-416)
-            const uint32_t i = (uint32_t)(i0 + u * stride);
-            const uint32_t sm = a.drop_seed + epoch * 0x9E3779B9u + (uint32_t)q * 0x85EBCA77u;
-            g[u].x = dropout_keep(sm, 4u * i + 0, drop_thresh) ? g[u].x : 0.f;
-            g[u].y = dropout_keep(sm, 4u * i + 1, drop_thresh) ? g[u].y : 0.f;
-            g[u].z = dropout_keep(sm, 4u * i + 2, drop_thresh) ? g[u].z : 0.f;
-            g[u].w = dropout_keep(sm, 4u * i + 3, drop_thresh) ? g[u].w : 0.f;
-          }
-          acc[u].x += g[u].x; acc[u].y += g[u].y; acc[u].z += g[u].z; acc[u].w += g[u].w;
-        }
-      }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int i = i0 + u * stride;
-        if (i < end) {
-          w[u].x -= scale * acc[u].x; w[u].y -= scale * acc[u].y;
-          w[u].z -= scale * acc[u].z; w[u].w -= scale * acc[u].w;
-          for (int q = 0; q < a.nranks; ++q) st_peer_f4(P.params[q] + 4 * (size_t)i, w[u]);
-          if (a.shadow != nullptr) {   // my shard's bf16 shadow straight from registers
-            uint2 o;
-            o.x = pack_bf16x2(w[u].x, w[u].y);
-            o.y = pack_bf16x2(w[u].z, w[u].w);
-            *reinterpret_cast<uint2*>(a.shadow + 4 * (size_t)i) = o;
+        if (i >= end) continue;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < SYNC_MAX_RANKS; ++c) {
+          if (c < nc) {
+            float4 v = g[u][c];
+            if (drop_thresh) {   // drop-connect: contributor's Bernoulli mask, no 1/p rescale (reference :414-416)
+              const uint32_t sm = a.drop_seed + epoch * 0x9E3779B9u + (uint32_t)contrib[c] * 0x85EBCA77u;
+              v.x = dropout_keep(sm, 4u * i + 0, drop_thresh) ? v.x : 0.f;
+              v.y = dropout_keep(sm, 4u * i + 1, drop_thresh) ? v.y : 0.f;
+              v.z = dropout_keep(sm, 4u * i + 2, drop_thresh) ? v.z : 0.f;
+              v.w = dropout_keep(sm, 4u * i + 3, drop_thresh) ? v.w : 0.f;
+            }
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
           }
+        }
+        float4 nw = w[u];
+        nw.x -= scale * acc.x; nw.y -= scale * acc.y; nw.z -= scale * acc.z; nw.w -= scale * acc.w;
+        for (int q = 0; q < a.nranks; ++q) st_peer_f4(P.params[q] + 4 * (size_t)i, nw);
+        if (a.shadow != nullptr) {   // my shard's bf16 shadow straight from registers
+          uint2 o;
+          o.x = pack_bf16x2(nw.x, nw.y);
+          o.y = pack_bf16x2(nw.z, nw.w);
+          *reinterpret_cast<uint2*>(a.shadow + 4 * (size_t)i) = o;
         }
       }
     }

@@ -24,6 +24,7 @@ calls cuDNN, cuBLAS or NCCL.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Tuple
 
 import numpy as np
@@ -80,6 +81,8 @@ class CudaLeNetEngine(ComputeEngine):
         self._loaded = 0
         self._h2d_bytes = B * 784 * 4 + B * 8
         self.copy_stream = torch.cuda.Stream(device=dev)
+        self._side = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        self._branches = os.environ.get("DMNIST_BRANCHES", "1") != "0"
         self._copy_done = [torch.cuda.Event() for _ in range(2)]
         self._slot_free = [torch.cuda.Event() for _ in range(2)]
         self._graphs = [None, None]
@@ -159,18 +162,43 @@ class CudaLeNetEngine(ComputeEngine):
         return 4
 
     def _launch_backward(self, images: torch.Tensor, B: int) -> int:
-        lib, sp, g, pb = self.lib, stream_ptr(), self.g, self.pb
-        # fc1 wgrad: dW1[3136,512] = a2^T (A MN-major) * dh (B MN-major), K = batch; straight into the arena
-        G.gemm_bf16_raw(self.a2, self.dh, g["fc1_weights"], 3136, 512, B, 3136, 512, 512, True, True,
-                        G.EPI_STORE_F32, bn=128)
+        """Backward as a small DAG: the two weight-gradient GEMMs have no consumer before the aggregation
+        kernel, so they run on side streams (captured as parallel graph branches) next to the data-gradient
+        chain fc1_dgrad -> unpool2 -> conv2_dgrad -> conv1_wgrad."""
+        lib, g, pb = self.lib, self.g, self.pb
+        main = torch.cuda.current_stream()
+        branch = self._branches
+        if branch:
+            fork1 = torch.cuda.Event()
+            fork1.record(main)
+            self._side[0].wait_event(fork1)
+        with torch.cuda.stream(self._side[0] if branch else main):
+            # fc1 wgrad: dW1[3136,512] = a2^T (A MN-major) * dh (B MN-major), K = batch; straight into the arena
+            G.gemm_bf16_raw(self.a2, self.dh, g["fc1_weights"], 3136, 512, B, 3136, 512, 512, True, True,
+                            G.EPI_STORE_F32, bn=128)
+            if branch:
+                join1 = torch.cuda.Event()
+                join1.record(self._side[0])
+        sp = stream_ptr()
         # fc1 dgrad: dxfc[B,3136] = dh[B,512] (K-major) * W1[3136,512] (rows = in, K = out contiguous)
         G.gemm_bf16_raw(self.dh, pb["fc1_weights"], self.dxfc, B, 3136, 512, 512, 512, 3136, False, False,
                         G.EPI_STORE_BF16, bn=64)
         check(lib.dm_unpool2(ptr(self.dxfc), ptr(self.code2), ptr(self.dy2), ptr(g["conv2_biases"]), B, sp), "unpool2")
-        check(lib.dm_conv2_wgrad(ptr(self.a1), ptr(self.dy2), ptr(g["conv2_weights"]), B, sp), "conv2_wgrad")
+        if branch:
+            fork2 = torch.cuda.Event()
+            fork2.record(main)
+            self._side[1].wait_event(fork2)
+        with torch.cuda.stream(self._side[1] if branch else main):
+            check(lib.dm_conv2_wgrad(ptr(self.a1), ptr(self.dy2), ptr(g["conv2_weights"]), B, stream_ptr()), "conv2_wgrad")
+            if branch:
+                join2 = torch.cuda.Event()
+                join2.record(self._side[1])
         check(lib.dm_conv2_dgrad(ptr(self.dy2), ptr(pb["conv2_weights"]), ptr(self.dx1), B, sp), "conv2_dgrad")
         check(lib.dm_conv1_wgrad(ptr(images), ptr(self.dx1), ptr(self.code1), ptr(g["conv1_weights"]),
                                  ptr(g["conv1_biases"]), B, sp), "conv1_wgrad")
+        if branch:
+            main.wait_event(join1)
+            main.wait_event(join2)
         return 6
 
     def _zero_args(self, train: bool):
@@ -272,7 +300,8 @@ class CudaLeNetEngine(ComputeEngine):
                 self._launch_step(s, False)           # warm-up (gradients only): sets func attributes outside capture
                 torch.cuda.synchronize()
                 gr = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gr, stream=torch.cuda.Stream(device=self.device)):
+                # thread_local: other threads (NCCL watchdog, pin-memory) may call CUDA while we capture
+                with torch.cuda.graph(gr, stream=torch.cuda.Stream(device=self.device), capture_error_mode="thread_local"):
                     self._launch_step(s, with_sync)
                 self._graphs[key] = (gr, with_sync)
             self._graphs[key][0].replay()

@@ -36,6 +36,49 @@ def test_single_rank_is_plain_sgd():
     be.check_error()
 
 
+def test_gradient_drop_connect_mask_in_the_load_stage():
+    """reference distributed_train.py:194-196,414-416: Bernoulli(p) 0/1 mask on every gradient element, no 1/p rescale."""
+    from distributedmnist_b200.models import dropout_keep_mask
+    from distributedmnist_b200.parallel.context import ReplicaContext
+    from distributedmnist_b200.parallel.fused import FusedBackend
+    be = FusedBackend(ReplicaContext(0, 1, 0, torch.device("cuda", 0), "none"))
+    n = 1 << 14
+    params, grads = be.allocate(n), be.allocate(n)
+    params.copy_(torch.randn(n, device="cuda"))
+    grads.copy_(torch.randn(n, device="cuda"))
+    be.drop_connect_(grads, 0.9, 0)
+    ref = params.clone()
+    for step in range(3):
+        mix = (be.drop_seed + step * 0x9E3779B9 + 0 * 0x85EBCA77) & 0xFFFFFFFF
+        keep = dropout_keep_mask(mix, 1, n, 0.9, device="cuda").view(-1)
+        ref -= 0.5 * grads * keep
+        be.sync_step(params, grads, 0.5, step, 1)
+        assert torch.allclose(params, ref, atol=1e-6)
+        assert 0.85 < keep.float().mean().item() < 0.95
+
+
+@pytest.mark.multigpu
+def test_k_of_n_training_through_the_reference_entrypoint(tmp_path):
+    """2 replicas, K=1, rank 1 delayed on the device every step: training proceeds at rank 0's pace,
+    rank 1's gradients are dropped, both logs show the same global steps."""
+    import re
+    import sys
+
+    from distributedmnist_b200.parallel.launcher import run_replicas
+    root = os.path.dirname(HERE)
+    codes = run_replicas([os.path.join(root, "src", "mnist_distributed_train.py"), "--job_name=worker",
+                          "--batch_size=64", "--max_steps=40", "--num_replicas_to_aggregate=1",
+                          "--inject_straggler=1:1.0:3000", "--initial_learning_rate=0.02",
+                          "--train_dir=" + str(tmp_path / "train_dir"), "--save_interval_secs=1000"],
+                         2, timeout=300, out_dir=str(tmp_path / "out"))
+    logs = {f: open(os.path.join(tmp_path, "out", f)).read() for f in sorted(os.listdir(tmp_path / "out"))}
+    assert codes == [0, 0], "\n".join(v[-1500:] for v in logs.values())
+    s0 = [int(x) for x in re.findall(r"Worker 0: .*: step ([0-9]+),", logs["out_master"])]
+    s1 = [int(x) for x in re.findall(r"Worker 1: .*: step ([0-9]+),", logs["out_worker_0"])]
+    assert s0 and s1 and max(s0) >= 40 and max(s1) >= 40
+    assert os.path.exists(tmp_path / "train_dir" / "checkpoint")
+
+
 @pytest.mark.multigpu
 def test_multi_rank_matches_nccl_and_masks_straggler(tmp_path):
     n = min(torch.cuda.device_count(), 8)
