@@ -1,0 +1,42 @@
+#!/bin/bash
+# One gpurun call = tests + bench (ours / torch baseline) + launch list + ncu full capture.
+# Usage (on the GPU box, from the repo root):  bash tools/gpu_round.sh [tests] [bench] [launches] [ncu]
+# Everything lands in gpurun_out/ (merged back by gpurun).
+set -u
+mkdir -p gpurun_out
+STAGES="${*:-tests bench launches ncu}"
+has() { [[ " $STAGES " == *" $1 "* ]]; }
+nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/nvsmi_start.csv 2>&1
+
+if has tests; then
+  timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
+  echo "pytest exit=$?" >> gpurun_out/pytest_gpu.log
+  tail -5 gpurun_out/pytest_gpu.log
+fi
+
+if has bench; then
+  nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap \
+      --format=csv -lms 200 > gpurun_out/clocks.csv 2>&1 &
+  SMI=$!
+  timeout 300 python bench.py --gpus 1 --steps 300 --warmup 20 --kernel-times > gpurun_out/bench_ours_1.json 2> gpurun_out/bench_ours_1.err
+  echo "bench ours exit=$?"; cat gpurun_out/bench_ours_1.json; grep KERNEL_TIMES gpurun_out/bench_ours_1.err
+  timeout 300 python bench.py --impl torch_ddp --gpus 1 --steps 300 --warmup 20 > gpurun_out/bench_torch_1.json 2> gpurun_out/bench_torch_1.err
+  echo "bench torch exit=$?"; cat gpurun_out/bench_torch_1.json
+  timeout 300 python bench.py --impl reference --gpus 1 > gpurun_out/bench_ref_1.json 2>&1
+  kill $SMI
+fi
+
+if has launches; then
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
+      --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 > gpurun_out/launches_run.log 2>&1
+  echo "ncu launches exit=$?"
+fi
+
+if has ncu; then
+  # two whole training steps of our kernels, full metric set, source-correlated
+  timeout 900 ncu --set full --clock-control none --import-source on \
+      -k regex:'conv1_|conv2_|gemm_tc|fc2_loss|unpool2|fused_sync' -s 36 -c 24 \
+      -f -o gpurun_out/lenet_step python bench.py --steps 3 --warmup 3 --no-graph > gpurun_out/ncu_full_run.log 2>&1
+  echo "ncu full exit=$?"
+  ls -la gpurun_out/
+fi
