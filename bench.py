@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--straggler", default="", help="rank:prob:usec device-side delay injection")
     ap.add_argument("--kernel-times", action="store_true", help="also print per-kernel device times (stderr)")
+    ap.add_argument("--trace", default="", help="after the timed runs: CUPTI timeline (torch.profiler) of a few graph-replayed "
+                                                "steps -> <path>.json (chrome trace) + <path>.txt (one step, kernel start/end)")
     return ap.parse_args()
 
 
@@ -58,7 +60,7 @@ class ClockSampler:
     REASONS = [(0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
                (0x4, "sw_power_cap"), (0x80, "hw_power_brake_slowdown"), (0x2, "applications_clocks_setting")]
 
-    def __init__(self, index: int, period_s: float = 0.02):
+    def __init__(self, index: int, period_s: float = 0.004):
         self.index, self.period = index, period_s
         self.sm, self.reasons, self.sm_max = [], set(), None
         self._stop = threading.Event()
@@ -106,6 +108,38 @@ def run_reference(args):
                       "unavailable": "reference is py2/TF<=1.0/Twisted with no setup.py; pip --no-index install fails "
                                      "and tensorflow/twisted are absent offline"}))
     return 0
+
+
+def write_timeline(path: str, step_fn, barrier, rank: int, steps: int = 6) -> None:
+    """Kernel timeline of graph-replayed steps (shows which kernels really overlap).  Never a bench value."""
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+    barrier()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        for i in range(steps):
+            step_fn(i)
+        torch.cuda.synchronize()
+    barrier()
+    if rank != 0:
+        return
+    os.makedirs(os.path.dirname(os.path.abspath(path)) or ".", exist_ok=True)
+    prof.export_chrome_trace(path + ".json")
+    ev = [e for e in json.load(open(path + ".json"))["traceEvents"]
+          if e.get("ph") == "X" and e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
+    ev.sort(key=lambda e: e["ts"])
+    # one step = from a conv1_fwd kernel to the next; print the second-to-last complete one
+    starts = [i for i, e in enumerate(ev) if "conv1_fwd" in e["name"] or "f32_to_bf16" in e["name"]]
+    with open(path + ".txt", "w") as f:
+        if len(starts) >= 3:
+            a, b = starts[-3], starts[-2]
+            t0 = ev[a]["ts"]
+            f.write("# one graph-replayed step: kernel, stream, start_us, end_us, dur_us (relative to the step's first kernel)\n")
+            for e in ev[a:b]:
+                f.write("%-44s s=%-4s %8.2f %8.2f %7.2f\n" % (e["name"].split("(")[0][-44:], e.get("args", {}).get("stream", "?"),
+                                                             e["ts"] - t0, e["ts"] + e["dur"] - t0, e["dur"]))
+            f.write("# step period = %.2f us\n" % (ev[b]["ts"] - t0))
+        else:
+            f.write("# no step boundary found; %d device events\n" % len(ev))
 
 
 def maybe_self_spawn(args) -> bool:
@@ -172,12 +206,9 @@ def main():
         torch.cuda.synchronize()
 
     def device_step(i: int):
-        # inputs come from the device pool (cold in L2); slot buffers are what the captured graph reads
-        s = i & 1
-        engine.images[s].copy_(d_imgs[i % pool_n].view(engine.images[s].shape))
-        engine.labels[s].copy_(d_lbls[i % pool_n])
-        engine._slot = s
-        engine._copy_done[s].record()
+        # inputs come from the device pool (cold in L2) through the same public call as the e2e path: the copy into the
+        # slot buffer runs on the engine's copy stream and overlaps the previous step
+        engine.load_batch(d_imgs[i % pool_n], d_lbls[i % pool_n])
         engine.train_step()
 
     def e2e_step(i: int):
@@ -236,6 +267,9 @@ def main():
             print("KERNEL_TIMES_US " + json.dumps({k: round(v, 2) for k, v in kt.items()}) + " sum=%.1f" % sum(kt.values()),
                   file=sys.stderr)
 
+    if args.trace:
+        write_timeline(args.trace, device_step, barrier, rank)
+
     if rank == 0:
         value = n * B * args.steps / (ms_total / 1e3)
         e2e_value = n * B * args.steps / (ms2_total / 1e3)
@@ -247,7 +281,9 @@ def main():
             "config": {"model": ("LeNet-like MNIST convnet (1,663,370 params, reference src/mnist.py)" if args.model == "lenet"
                                  else "%s hidden=%d (%d params)" % (args.model, args.hidden, engine.spec.num_trainable)),
                        "global_batch": n * B, "batch_per_replica": B, "seq_len": None,
-                       "parallelism": "dp%d (sync replicas, K=%d of %d, fused NVLink allreduce+SGD kernel)" % (n, k, n),
+                       "parallelism": "dp%d (sync replicas, K=%d of %d, fused NVLink allreduce+SGD kernel, %s)"
+                                      % (n, k, n, "NVLS multimem.ld_reduce/st" if backend.nvls_active else
+                                         ("P2P ld/st" if n > 1 else "single replica")),
                        "optimizer": "SGD, staircase exp-decay LR evaluated on device",
                        "l2": "inputs rotate through a %d MB device pool (> 126 MB L2)" % int(d_imgs.numel() * 4 / 1e6),
                        "cuda_graph": not args.no_graph},

@@ -43,6 +43,14 @@ DMNIST_DEVICE uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// prmt.b32, generic mode: result byte i = byte (sel nibble i & 7) of {b:a}; nibble bit 3 set -> the selected byte's
+// sign bit replicated over the result byte (0x00 / 0xff): turns per-byte flags into lane masks.
+DMNIST_DEVICE uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
 // 16-byte vector reduction into global memory (sm_90+): one instruction adds four consecutive floats.
 DMNIST_DEVICE void red_add_f32x4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");

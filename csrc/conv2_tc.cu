@@ -327,7 +327,7 @@ conv2_dgrad_kernel(const __grid_constant__ CUtensorMap tmDY,  // dY NHWC [B,14,1
 //     group 5     : taps (kh = 4, kw = 0..3)   -> chunk stride = one pixel     =  64 B
 //     group 6     : tap  (kh = 4, kw = 4) + three padding chunks (computed, never stored)
 // ------------------------------------------------------------------------------------------------------
-constexpr int WG_STAGES = 6;
+constexpr int WG_STAGES = 4;   // 4 x 32 KB: leaves room for two conv1_wgrad CTAs (37 KB each) on the same SM
 constexpr int WG_A_BYTES = 20 * 12 * 32 * 2;   // 15 KB patch
 constexpr int WG_B_BYTES = 128 * 64 * 2;       // 16 KB dY tile
 constexpr int WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES + 1024;   // keep the dY tile 1024-aligned (128B swizzle)

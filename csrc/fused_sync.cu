@@ -83,6 +83,10 @@ struct SyncArgs {
   uint32_t drop_seed;
   unsigned long long timeout_ns;
   __nv_bfloat16* shadow;      // local bf16 copy of the parameter arena (tensor-core operand source)
+  // NVLS (NVSwitch multicast) views of the two arenas, null when the fabric has none.  A load from mc_grads returns the
+  // SUM over all ranks computed inside the switch; a store to mc_params lands in every rank's arena.
+  const float* mc_grads;
+  float* mc_params;
 };
 
 // ---- system-scope memory helpers ----------------------------------------------------------------
@@ -112,6 +116,22 @@ DMNIST_DEVICE float4 ld_peer_f4(const float* p) {   // peer data: read once, kee
 }
 DMNIST_DEVICE void st_peer_f4(float* p, float4 v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+
+// In-switch reduction: one 16-byte load returns the element-wise fp32 sum of the same address on every rank.
+DMNIST_DEVICE float4 multimem_ld_reduce_f4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+// Multicast store: the switch replicates the 16 bytes into every rank's copy.
+DMNIST_DEVICE void multimem_st_f4(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
                "f"(v.w)
                : "memory");
 }
@@ -260,6 +280,38 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_sgd_kernel(SyncPee
     for (int q = 0; q < a.nranks; ++q)
       if ((mask >> q) & 1u) contrib[nc++] = q;
     const float* wsrc = P.params[a.rank];
+    const uint32_t full_mask = (1u << a.nranks) - 1u;
+    if (a.mc_grads != nullptr && a.mc_params != nullptr && !solo && mask == full_mask && drop_thresh == 0u) {
+      // ---- NVLS path (every replica contributes): the reduction happens inside the NVSwitch and the update is
+      // multicast back, so each GPU's links carry |shard| once in and once out instead of (N-1) x |shard| each way.
+      constexpr int V = 4;
+      const int stride = gridDim.x * SYNC_THREADS;
+      for (int i0 = begin + blockIdx.x * SYNC_THREADS + threadIdx.x; i0 < end; i0 += V * stride) {
+        float4 g[V], w[V];
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+          const int i = i0 + u * stride;
+          if (i < end) {
+            g[u] = multimem_ld_reduce_f4(a.mc_grads + 4 * (size_t)i);
+            w[u] = *reinterpret_cast<const float4*>(wsrc + 4 * (size_t)i);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+          const int i = i0 + u * stride;
+          if (i >= end) continue;
+          float4 nw = w[u];
+          nw.x -= scale * g[u].x; nw.y -= scale * g[u].y; nw.z -= scale * g[u].z; nw.w -= scale * g[u].w;
+          multimem_st_f4(a.mc_params + 4 * (size_t)i, nw);
+          if (a.shadow != nullptr) {
+            uint2 o;
+            o.x = pack_bf16x2(nw.x, nw.y);
+            o.y = pack_bf16x2(nw.z, nw.w);
+            *reinterpret_cast<uint2*>(a.shadow + 4 * (size_t)i) = o;
+          }
+        }
+      }
+    } else {
     // Latency is the enemy here (a remote load is ~2 us): every thread issues the loads of ALL contributors
     // for U elements before it touches any of them, so one NVLink round trip covers the whole reduction of
     // its elements (at N = 8 a shard is so small that most threads make exactly one trip).
@@ -305,6 +357,7 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_sgd_kernel(SyncPee
         }
       }
     }
+    }   // P2P path
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) me->t_phase[2] = globaltimer_ns();
 
@@ -397,7 +450,8 @@ int dm_sync_ctrl_offset(const char* field) {
 // peers: arrays of `nranks` device pointers (index = rank; own entries are the local buffers).
 int dm_fused_sync_sgd(void* const* ctrl, void* const* params, void* const* grads, int rank, int nranks, int k,
                       long long numel, float lr0, float decay_rate, int decay_steps, float drop_keep,
-                      unsigned int drop_seed, double timeout_ms, void* shadow_bf16, int ctas, void* stream_) {
+                      unsigned int drop_seed, double timeout_ms, void* shadow_bf16, int ctas, void* stream_,
+                      const void* mc_grads, void* mc_params) {
   using namespace dm;
   if (nranks < 1 || nranks > SYNC_MAX_RANKS || (numel & 3) || k < 1 || k > nranks) return -1;
   SyncPeers P;
@@ -413,6 +467,8 @@ int dm_fused_sync_sgd(void* const* ctrl, void* const* params, void* const* grads
   a.drop_keep = drop_keep; a.drop_seed = drop_seed;
   a.timeout_ns = (unsigned long long)(timeout_ms * 1e6);
   a.shadow = reinterpret_cast<__nv_bfloat16*>(shadow_bf16);
+  a.mc_grads = reinterpret_cast<const float*>(mc_grads);
+  a.mc_params = reinterpret_cast<float*>(mc_params);
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (ctas < 1) ctas = 64;
   if (k < nranks) return (int)launch_kernel(fused_sync_sgd_kernel<true>, dim3(ctas), dim3(SYNC_THREADS), 0, stream, P, a);

@@ -22,7 +22,12 @@ constexpr int GEMM_BK = 64;
 constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_THREADS = 192;
 
-enum GemmEpilogue : int { EPI_STORE_F32 = 0, EPI_ATOMIC_F32 = 1, EPI_STORE_BF16 = 2, EPI_BIAS_RELU_BF16 = 3 };
+enum GemmEpilogue : int { EPI_STORE_F32 = 0, EPI_ATOMIC_F32 = 1, EPI_STORE_BF16 = 2, EPI_BIAS_RELU_BF16 = 3,
+                          // fc1 dgrad fused with the backward of maxpool2 + ReLU2 (reference K4/K3 gradients): a 64-column
+                          // tile is one pooled position x 64 channels; the epilogue scatters each value to the argmax
+                          // pixel of its 2x2 window (dense bf16 [B,14,14,64], zeros elsewhere) and reduces the conv2
+                          // bias gradient -- the separate unpool kernel and the [B,3136] intermediate disappear.
+                          EPI_UNPOOL2_BF16 = 4 };
 
 struct GemmParams {
   int M, N;        // logical output extent (predication)
@@ -31,6 +36,8 @@ struct GemmParams {
   void* out;
   long long split_stride;   // EPI_STORE_F32 with split-K: split z writes its partial tile at out + z*split_stride
   const float* bias;        // EPI_BIAS_RELU_BF16: per-column bias (reference K2/K3 fused into the producer)
+  const uint8_t* code;      // EPI_UNPOOL2_BF16: pooling codes [M][N] (bits 0-1 argmax position, bit 2 ReLU active)
+  float* g_bias;            // EPI_UNPOOL2_BF16: conv2 bias gradient [64], accumulated atomically (pre-zeroed)
 };
 
 template <int BN>
@@ -42,8 +49,13 @@ struct GemmSmem {
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + alignment slack
 };
 
+// The unpool epilogue is instruction-heavy: it gets eight epilogue warps (two per TMEM lane quarter, one 32-column
+// chunk each) instead of four, so two warps share every scheduler and hide each other's latencies.
+template <int EPI>
+constexpr int gemm_threads() { return EPI == EPI_UNPOOL2_BF16 ? GEMM_THREADS + 128 : GEMM_THREADS; }
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads<EPI>(), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
   using S = GemmSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -139,12 +151,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------ epilogue -----------------------------------
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
     const int row = m0 + q * 32 + lane;
+    const int c_begin = EPI == EPI_UNPOOL2_BF16 ? (warp - 2) >> 2 : 0;
+    const int c_end = EPI == EPI_UNPOOL2_BF16 ? c_begin + 1 : BN / 32;
+    uint32_t cw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    if (EPI == EPI_UNPOOL2_BF16 && row < p.M) {
+      // pooling codes of this thread's 32 channels: an input of the forward pass, fetched while the MMAs run
+      const uint4* cp = reinterpret_cast<const uint4*>(p.code + (size_t)row * p.N + n0 + c_begin * 32);
+      const uint4 c0 = __ldg(cp), c1 = __ldg(cp + 1);
+      cw[0] = c0.x; cw[1] = c0.y; cw[2] = c0.z; cw[3] = c0.w; cw[4] = c1.x; cw[5] = c1.y; cw[6] = c1.z; cw[7] = c1.w;
+    }
     if (nkb > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after_sync();
     }
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = c_begin; c < c_end; ++c) {
       uint32_t v[32];
       if (nkb > 0) {
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
@@ -178,6 +199,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 32; ++j)
               if (col0 + j < p.N) atomicAdd(o + j, __uint_as_float(v[j]));
           }
+        } else if (EPI == EPI_UNPOOL2_BF16) {
+          // handled below (needs the whole warp, also for rows beyond M)
         } else {
           if (EPI == EPI_BIAS_RELU_BF16) {
 #pragma unroll
@@ -203,6 +226,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+      if (EPI == EPI_UNPOOL2_BF16) {
+        // thread = batch row, 32 consecutive channels (ch0 ..) of pooled position `pos`
+        const int pos = col0 >> 6, ch0 = col0 & 63;
+        const int ph = pos / 7, pw = pos - ph * 7;
+        float gs[32];                                   // masked gradient (bias-gradient contribution)
+        if (row < p.M) {
+          // code byte = argmax position (bits 0-1) | ReLU active (bit 2).  Byte-parallel: for window position q4,
+          // x = (codes & 7) ^ (4 | q4) is zero exactly in the matching bytes; x + 0x7f sets bit 7 of the others
+          // (no carries: x < 8), so ~(x + 0x7f..) & 0x80.. flags the matches and PRMT's sign-replicate mode widens
+          // each flag to a 16-bit lane mask for the packed bf16 pairs.
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+#pragma unroll
+          for (int j = 0; j < 32; ++j) gs[j] = ((cw[j >> 2] >> ((j & 3) * 8)) & 4u) ? __uint_as_float(v[j]) : 0.f;
+          __nv_bfloat16* dy = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {              // the four pixels of the 2x2 window: 64 B each
+            const int y = 2 * ph + (q4 >> 1), x = 2 * pw + (q4 & 1);
+            uint4* dst = reinterpret_cast<uint4*>(dy + (((size_t)row * 14 + y) * 14 + x) * 64 + ch0);
+            uint32_t o[16];
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) {            // code word w8 <-> channels 4*w8 .. 4*w8+3 <-> pk[2*w8], pk[2*w8+1]
+              const uint32_t xz = (cw[w8] & 0x07070707u) ^ (0x04040404u | (0x01010101u * (uint32_t)q4));
+              const uint32_t hit = ~(xz + 0x7f7f7f7fu) & 0x80808080u;
+              o[2 * w8] = pk[2 * w8] & prmt(hit, 0u, 0x9988u);          // bytes {0,0,1,1} sign-replicated
+              o[2 * w8 + 1] = pk[2 * w8 + 1] & prmt(hit, 0u, 0xbbaau);  // bytes {2,2,3,3}
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dst[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) gs[j] = 0.f;
+        }
+        // column sums over the warp's 32 rows: butterfly transpose-reduce (31 shuffles), lane l ends with channel ch0 + l
+#pragma unroll
+        for (int st = 0; st < 5; ++st) {
+          const int off = 16 >> st;                     // compile-time after unrolling: gs[] stays in registers
+          const bool upper = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (i < off) {
+              const float send = upper ? gs[i] : gs[i + off];
+              const float keep = upper ? gs[i + off] : gs[i];
+              gs[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+        }
+        atomicAdd(p.g_bias + ch0 + lane, gs[0]);
+      }
     }
   }
 
@@ -225,7 +299,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     configured = true;
   }
   dim3 grid((p.M + GEMM_BM - 1) / GEMM_BM, (p.N + BN - 1) / BN, splits);
-  return (int)launch_kernel(kern, grid, dim3(GEMM_THREADS), smem, stream, tmA, tmB, p);
+  return (int)launch_kernel(kern, grid, dim3(gemm_threads<EPI>()), smem, stream, tmA, tmB, p);
 }
 
 template <int BN, int EPI>
@@ -263,7 +337,7 @@ extern "C" int dm_gemm_bf16(const void* A, const void* B, void* out, int M, int 
   else       rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, 64, 128);
   if (rc) return 200 + rc;
   GemmParams p{M, N, (K + GEMM_BK - 1) / GEMM_BK, ldo, out, splits > 1 ? split_stride : 0,
-               reinterpret_cast<const float*>(bias)};
+               reinterpret_cast<const float*>(bias), nullptr, nullptr};
   if (splits > p.num_kb && epi == EPI_ATOMIC_F32) splits = p.num_kb > 0 ? p.num_kb : 1;
 #define DM_DISPATCH(BN_, EPI_) return dispatch_major<BN_, EPI_>(a_mn != 0, b_mn != 0, tmA, tmB, p, splits, stream)
   if (bn == 64) {
@@ -278,4 +352,21 @@ extern "C" int dm_gemm_bf16(const void* A, const void* B, void* out, int M, int 
     DM_DISPATCH(128, 3);
   }
 #undef DM_DISPATCH
+}
+
+// fc1 dgrad fused with the maxpool2/ReLU2 backward and the conv2 bias gradient:
+//   dxfc[b, j] = sum_k dh[b, k] * W1[j, k]   (A = dh [B,512] K-major, B = W1 [3136,512] rows = j, K contiguous)
+//   dy2[b, 2ph+dy, 2pw+dx, c] = dxfc[b, (ph*7+pw)*64 + c] where code says (dy,dx) is the argmax and ReLU was active
+//   g_bias2[c] += sum of the scattered values.          dy2: [B,14,14,64] bf16, fully written (zeros included).
+extern "C" int dm_fc1_dgrad_unpool(const void* dh, const void* w1_bf16, const void* code2, void* dy2, void* g_bias2, int B,
+                                   void* stream_) {
+  using namespace dm;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d_bf16(&tmA, dh, 512, (uint64_t)B, 512, 64, 128, 128);
+  if (rc) return 100 + rc;
+  rc = make_tmap_2d_bf16(&tmB, w1_bf16, 512, 3136, 512, 64, 64, 128);
+  if (rc) return 200 + rc;
+  GemmParams p{B, 3136, 512 / GEMM_BK, 0, dy2, 0, nullptr, reinterpret_cast<const uint8_t*>(code2),
+               reinterpret_cast<float*>(g_bias2)};
+  return launch_gemm<64, false, false, EPI_UNPOOL2_BF16>(tmA, tmB, p, 1, reinterpret_cast<cudaStream_t>(stream_));
 }

@@ -1,10 +1,17 @@
 #include "host_utils.h"
 
+#include <stdlib.h>
+
 #include <mutex>
 
 namespace dm {
 
 int g_pdl = 0;
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v != nullptr && *v != 0) ? atoi(v) : dflt;
+}
 
 void* driver_symbol(const char* name) {
   void* fn = nullptr;

@@ -7,8 +7,9 @@ Step = (reference src/distributed_train.py:332 ``sess.run(apply_gradients_op)``)
     conv1_fwd        conv+bias+ReLU+pool (SIMT, K=25)       csrc/lenet_simt.cu
     conv2_fwd        tcgen05 implicit GEMM + bias/ReLU/pool csrc/conv2_tc.cu
     fc1_fwd          tcgen05 GEMM, split-K into fp32        csrc/gemm_tc.cu
-    fc2_loss         bias+ReLU+dropout, fc2, softmax-CE,
-                     accuracy, and their backward           csrc/lenet_simt.cu
+    fc2_fwd_bwd      bias+ReLU+dropout, fc2, softmax-CE,
+                     accuracy, dlogits, d(fc1)              csrc/lenet_simt.cu
+    fc2_wgrad        fc2 weight/bias + fc1 bias gradients   (side branch)
     fc1_wgrad        tcgen05 GEMM (MN-major x MN-major) -> gradient arena
     fc1_dgrad        tcgen05 GEMM -> bf16
     unpool2          maxpool2/ReLU2 backward + conv2 bias grad
@@ -70,6 +71,8 @@ class CudaLeNetEngine(ComputeEngine):
         self.fc1_splits = 7                                         # 49 k-blocks of 64 -> 7 per CTA
         self.h_part = torch.zeros(self.fc1_splits, B, 512, dtype=f32, device=dev)   # fc1 split-K partial sums
         self.dh = torch.zeros(B, 512, dtype=bf, device=dev)
+        self.h_act = torch.zeros(B, 512, dtype=f32, device=dev)      # post ReLU/dropout fc1 activations (fc2_wgrad operand)
+        self.dlogits = torch.zeros(B, 12, dtype=f32, device=dev)     # d loss / d logits, 48-byte rows
         self.dxfc = torch.zeros(B, 3136, dtype=bf, device=dev)
         self.dy2 = torch.zeros(B, 14, 14, 64, dtype=bf, device=dev)
         self.dx1 = torch.zeros(B, 14, 14, 32, dtype=bf, device=dev)
@@ -81,8 +84,14 @@ class CudaLeNetEngine(ComputeEngine):
         self._loaded = 0
         self._h2d_bytes = B * 784 * 4 + B * 8
         self.copy_stream = torch.cuda.Stream(device=dev)
-        self._side = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        # the data-gradient chain is the critical path: it is captured on a high-priority stream, the weight-gradient
+        # side branches on low-priority ones, so the block scheduler serves the chain first whenever both have CTAs pending
+        lo, hi = (0, -1)
+        self._side = [torch.cuda.Stream(device=dev, priority=lo) for _ in range(2)]
+        self._main_priority = hi if os.environ.get("DMNIST_PRIO", "1") != "0" else lo
+        self._wgrad_late = os.environ.get("DMNIST_WGRAD_LATE", "1") != "0"
         self._branches = os.environ.get("DMNIST_BRANCHES", "1") != "0"
+        self._fuse_unpool = os.environ.get("DMNIST_FUSE_UNPOOL", "1") != "0"
         self._copy_done = [torch.cuda.Event() for _ in range(2)]
         self._slot_free = [torch.cuda.Event() for _ in range(2)]
         self._graphs = [None, None]
@@ -99,9 +108,9 @@ class CudaLeNetEngine(ComputeEngine):
     def load_batch(self, images, labels) -> None:
         """Pinned host staging -> device slot, on the copy stream (overlaps the previous step)."""
         s = self._loaded & 1
-        if isinstance(images, torch.Tensor) and images.is_pinned() and labels.is_pinned() \
-                and images.dtype == torch.float32 and labels.dtype == torch.int64:
-            # already page-locked: DMA straight from the caller's buffers (they must stay untouched
+        if isinstance(images, torch.Tensor) and images.dtype == torch.float32 and labels.dtype == torch.int64 \
+                and ((images.is_pinned() and labels.is_pinned()) or (images.is_cuda and labels.is_cuda)):
+            # already page-locked (or device-resident): DMA straight from the caller's buffers (they must stay untouched
             # until the copy has run, i.e. until the step that consumes them has been enqueued twice)
             hi, hl = images.view(self.images[0].shape), labels
         else:
@@ -149,16 +158,15 @@ class CudaLeNetEngine(ComputeEngine):
         check(lib.dm_conv2_fwd(ptr(self.a1), ptr(pb["conv2_weights"]), ptr(p["conv2_biases"]), ptr(self.a2),
                                ptr(self.code2), B, sp), "conv2_fwd")
         # fc1: a2[B,3136] (K-major) * W1[3136,512] (MN-major), split-K: 7 partial tiles stored side by side
-        # (no atomics, nothing to zero); fc2_loss sums them while applying bias + ReLU + dropout
+        # (no atomics, nothing to zero); fc2_fwd_bwd sums them while applying bias + ReLU + dropout
         stride = self.h_part.stride(0)
         G.gemm_bf16_raw(self.a2, pb["fc1_weights"], self.h_part, B, 512, 3136, 3136, 512, 512, False, True,
                         G.EPI_STORE_F32, splits=self.fc1_splits, bn=64, split_stride=stride)
-        check(lib.dm_fc2_loss(ptr(self.h_part), ctypes.c_longlong(stride), self.fc1_splits, ptr(p["fc1_biases"]),
-                              ptr(p["fc2_weights"]), ptr(p["fc2_biases"]), ptr(labels), ptr(self.dh),
-                              ptr(self.g["fc2_weights"]), ptr(self.g["fc2_biases"]), ptr(self.g["fc1_biases"]),
-                              ptr(self.d_loss_acc), ptr(logits_out), B, int(train), ctypes.c_uint(self._seed_mix0),
-                              self._epoch_ptr if train else ctypes.c_void_p(0), ctypes.c_float(self.keep_prob), sp),
-              "fc2_loss")
+        check(lib.dm_fc2_fwd_bwd(ptr(self.h_part), ctypes.c_longlong(stride), self.fc1_splits, ptr(p["fc1_biases"]),
+                                 ptr(p["fc2_weights"]), ptr(p["fc2_biases"]), ptr(labels), ptr(self.dh), ptr(self.h_act),
+                                 ptr(self.dlogits), ptr(self.d_loss_acc), ptr(logits_out), B, int(train),
+                                 ctypes.c_uint(self._seed_mix0), self._epoch_ptr if train else ctypes.c_void_p(0),
+                                 ctypes.c_float(self.keep_prob), sp), "fc2_fwd_bwd")
         return 4
 
     def _launch_backward(self, images: torch.Tensor, B: int) -> int:
@@ -176,14 +184,27 @@ class CudaLeNetEngine(ComputeEngine):
             # fc1 wgrad: dW1[3136,512] = a2^T (A MN-major) * dh (B MN-major), K = batch; straight into the arena
             G.gemm_bf16_raw(self.a2, self.dh, g["fc1_weights"], 3136, 512, B, 3136, 512, 512, True, True,
                             G.EPI_STORE_F32, bn=128)
+            # fc2 weight/bias + fc1 bias gradients: only the aggregation kernel consumes them
+            check(lib.dm_fc2_wgrad(ptr(self.h_act), ptr(self.dlogits), ptr(self.dh), ptr(g["fc2_weights"]),
+                                   ptr(g["fc2_biases"]), ptr(g["fc1_biases"]), B, stream_ptr()), "fc2_wgrad")
             if branch:
                 join1 = torch.cuda.Event()
                 join1.record(self._side[0])
         sp = stream_ptr()
         # fc1 dgrad: dxfc[B,3136] = dh[B,512] (K-major) * W1[3136,512] (rows = in, K = out contiguous)
-        G.gemm_bf16_raw(self.dh, pb["fc1_weights"], self.dxfc, B, 3136, 512, 512, 512, 3136, False, False,
-                        G.EPI_STORE_BF16, bn=64)
-        check(lib.dm_unpool2(ptr(self.dxfc), ptr(self.code2), ptr(self.dy2), ptr(g["conv2_biases"]), B, sp), "unpool2")
+        if self._fuse_unpool:
+            # ... with maxpool2/ReLU2 backward and the conv2 bias gradient in the GEMM epilogue (no [B,3136] intermediate)
+            check(lib.dm_fc1_dgrad_unpool(ptr(self.dh), ptr(pb["fc1_weights"]), ptr(self.code2), ptr(self.dy2),
+                                          ptr(g["conv2_biases"]), B, sp), "fc1_dgrad_unpool")
+        else:
+            G.gemm_bf16_raw(self.dh, pb["fc1_weights"], self.dxfc, B, 3136, 512, 512, 512, 3136, False, False,
+                            G.EPI_STORE_BF16, bn=64)
+            check(lib.dm_unpool2(ptr(self.dxfc), ptr(self.code2), ptr(self.dy2), ptr(g["conv2_biases"]), B, sp), "unpool2")
+        late = branch and self._wgrad_late
+        if late:
+            # conv2 dgrad and wgrad each fill the machine (1 CTA/SM, ~200 KB smem): side by side they only slow the chain
+            # down.  wgrad is forked AFTER dgrad instead and shares the SMs with conv1_wgrad (LDS/FMA-bound, 37 KB/CTA).
+            check(lib.dm_conv2_dgrad(ptr(self.dy2), ptr(pb["conv2_weights"]), ptr(self.dx1), B, sp), "conv2_dgrad")
         if branch:
             fork2 = torch.cuda.Event()
             fork2.record(main)
@@ -193,13 +214,14 @@ class CudaLeNetEngine(ComputeEngine):
             if branch:
                 join2 = torch.cuda.Event()
                 join2.record(self._side[1])
-        check(lib.dm_conv2_dgrad(ptr(self.dy2), ptr(pb["conv2_weights"]), ptr(self.dx1), B, sp), "conv2_dgrad")
+        if not late:
+            check(lib.dm_conv2_dgrad(ptr(self.dy2), ptr(pb["conv2_weights"]), ptr(self.dx1), B, sp), "conv2_dgrad")
         check(lib.dm_conv1_wgrad(ptr(images), ptr(self.dx1), ptr(self.code1), ptr(g["conv1_weights"]),
                                  ptr(g["conv1_biases"]), B, sp), "conv1_wgrad")
         if branch:
             main.wait_event(join1)
             main.wait_event(join2)
-        return 6
+        return 6 if self._fuse_unpool else 7
 
     def _zero_args(self, train: bool):
         """Regions conv1_fwd clears at the start of a training step (atomically accumulated gradients + loss)."""
@@ -216,7 +238,7 @@ class CudaLeNetEngine(ComputeEngine):
     def time_kernels(self, iters: int = 20) -> dict:
         """Average device time of every kernel of the step, measured in place with CUDA events between
         eager launches (caches warm, as in the replayed graph; includes the launch gap)."""
-        names = ["memsets", "conv1_fwd", "conv2_fwd", "fc1_fwd", "fc2_loss", "fc1_wgrad", "fc1_dgrad", "unpool2",
+        names = ["memsets", "conv1_fwd", "conv2_fwd", "fc1_fwd", "fc2_fwd_bwd", "fc1_wgrad", "fc2_wgrad", "fc1_dgrad", "unpool2",
                  "conv2_wgrad", "conv2_dgrad", "conv1_wgrad", "fused_sync_sgd"]
         tot = {n: 0.0 for n in names}
         B, s = self.batch_size, self._slot
@@ -236,17 +258,25 @@ class CudaLeNetEngine(ComputeEngine):
             yield "fc1_fwd", lambda: G.gemm_bf16_raw(self.a2, pb["fc1_weights"], self.h_part, B, 512, 3136, 3136, 512, 512,
                                                      False, True, G.EPI_STORE_F32, splits=self.fc1_splits, bn=64,
                                                      split_stride=stride)
-            yield "fc2_loss", lambda: check(lib.dm_fc2_loss(
+            yield "fc2_fwd_bwd", lambda: check(lib.dm_fc2_fwd_bwd(
                 ptr(self.h_part), ctypes.c_longlong(stride), self.fc1_splits, ptr(p["fc1_biases"]), ptr(p["fc2_weights"]),
-                ptr(p["fc2_biases"]), ptr(lbl), ptr(self.dh), ptr(g["fc2_weights"]), ptr(g["fc2_biases"]),
-                ptr(g["fc1_biases"]), ptr(self.d_loss_acc), ctypes.c_void_p(0), B, 1, ctypes.c_uint(self._seed_mix0),
-                self._epoch_ptr, ctypes.c_float(self.keep_prob), sp), "fc2_loss")
+                ptr(p["fc2_biases"]), ptr(lbl), ptr(self.dh), ptr(self.h_act), ptr(self.dlogits), ptr(self.d_loss_acc),
+                ctypes.c_void_p(0), B, 1, ctypes.c_uint(self._seed_mix0), self._epoch_ptr, ctypes.c_float(self.keep_prob), sp),
+                "fc2_fwd_bwd")
             yield "fc1_wgrad", lambda: G.gemm_bf16_raw(self.a2, self.dh, g["fc1_weights"], 3136, 512, B, 3136, 512, 512,
                                                        True, True, G.EPI_STORE_F32, bn=128)
-            yield "fc1_dgrad", lambda: G.gemm_bf16_raw(self.dh, pb["fc1_weights"], self.dxfc, B, 3136, 512, 512, 512, 3136,
-                                                       False, False, G.EPI_STORE_BF16, bn=64)
-            yield "unpool2", lambda: check(lib.dm_unpool2(ptr(self.dxfc), ptr(self.code2), ptr(self.dy2),
-                                                          ptr(g["conv2_biases"]), B, sp), "unpool2")
+            yield "fc2_wgrad", lambda: check(lib.dm_fc2_wgrad(ptr(self.h_act), ptr(self.dlogits), ptr(self.dh),
+                                                              ptr(g["fc2_weights"]), ptr(g["fc2_biases"]),
+                                                              ptr(g["fc1_biases"]), B, sp), "fc2_wgrad")
+            if self._fuse_unpool:
+                yield "fc1_dgrad", lambda: check(lib.dm_fc1_dgrad_unpool(ptr(self.dh), ptr(pb["fc1_weights"]), ptr(self.code2),
+                                                                         ptr(self.dy2), ptr(g["conv2_biases"]), B, sp),
+                                                 "fc1_dgrad_unpool")
+            else:
+                yield "fc1_dgrad", lambda: G.gemm_bf16_raw(self.dh, pb["fc1_weights"], self.dxfc, B, 3136, 512, 512, 512, 3136,
+                                                           False, False, G.EPI_STORE_BF16, bn=64)
+                yield "unpool2", lambda: check(lib.dm_unpool2(ptr(self.dxfc), ptr(self.code2), ptr(self.dy2),
+                                                              ptr(g["conv2_biases"]), B, sp), "unpool2")
             yield "conv2_wgrad", lambda: check(lib.dm_conv2_wgrad(ptr(self.a1), ptr(self.dy2), ptr(g["conv2_weights"]), B, sp),
                                                "conv2_wgrad")
             yield "conv2_dgrad", lambda: check(lib.dm_conv2_dgrad(ptr(self.dy2), ptr(pb["conv2_weights"]), ptr(self.dx1), B, sp),
@@ -301,7 +331,8 @@ class CudaLeNetEngine(ComputeEngine):
                 torch.cuda.synchronize()
                 gr = torch.cuda.CUDAGraph()
                 # thread_local: other threads (NCCL watchdog, pin-memory) may call CUDA while we capture
-                with torch.cuda.graph(gr, stream=torch.cuda.Stream(device=self.device), capture_error_mode="thread_local"):
+                cap = torch.cuda.Stream(device=self.device, priority=getattr(self, "_main_priority", 0))
+                with torch.cuda.graph(gr, stream=cap, capture_error_mode="thread_local"):
                     self._launch_step(s, with_sync)
                 self._graphs[key] = (gr, with_sync)
             self._graphs[key][0].replay()

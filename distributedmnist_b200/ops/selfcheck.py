@@ -121,9 +121,13 @@ def check_fc2_loss(B: int = 64, seed: int = 4) -> List[Result]:
     logits = torch.zeros(B, 10, device=dev)
     # the kernel consumes split-K partial sums: hand it three partials that add up to h_pre
     parts = torch.stack([h_pre * 0.5, h_pre * 0.25, h_pre * 0.25]).contiguous()
-    check(lib.dm_fc2_loss(ptr(parts), ctypes.c_longlong(parts.stride(0)), 3, ptr(b1), ptr(w2), ptr(b2), ptr(labels),
-                          ptr(dh), ptr(gw2), ptr(gb2), ptr(gb1), ptr(la), ptr(logits), B, 1, ctypes.c_uint(mix0),
-                          ptr(step), ctypes.c_float(0.5), stream_ptr()), "fc2_loss")
+    h_act = torch.zeros(B, 512, device=dev)
+    dl = torch.zeros(B, 12, device=dev)
+    check(lib.dm_fc2_fwd_bwd(ptr(parts), ctypes.c_longlong(parts.stride(0)), 3, ptr(b1), ptr(w2), ptr(b2), ptr(labels),
+                             ptr(dh), ptr(h_act), ptr(dl), ptr(la), ptr(logits), B, 1, ctypes.c_uint(mix0), ptr(step),
+                             ctypes.c_float(0.5), stream_ptr()), "fc2_fwd_bwd")
+    gw2.fill_(7.0), gb2.fill_(7.0), gb1.fill_(7.0)          # plain stores: stale contents must not matter
+    check(lib.dm_fc2_wgrad(ptr(h_act), ptr(dl), ptr(dh), ptr(gw2), ptr(gb2), ptr(gb1), B, stream_ptr()), "fc2_wgrad")
     # reference
     hpre = (h_pre + b1).requires_grad_(True)
     keep = dropout_keep_mask(mix, B, 512, 0.5, device=dev)
@@ -137,6 +141,29 @@ def check_fc2_loss(B: int = 64, seed: int = 4) -> List[Result]:
             ("fc2.dh", (dh.float() - hpre.grad).abs().max().item(), 2e-4 + 0.01 * hpre.grad.abs().max().item()),
             ("fc2.g_w2", (gw2 - w2r.grad).abs().max().item(), 1e-4), ("fc2.g_b2", (gb2 - b2r.grad).abs().max().item(), 1e-5),
             ("fc2.g_b1", (gb1 - hpre.grad.sum(0)).abs().max().item(), 1e-3)]
+
+
+def check_fc1_dgrad_unpool(B: int = 200, seed: int = 6) -> List[Result]:
+    """fc1 dgrad GEMM with the maxpool2/ReLU2 backward + conv2 bias gradient fused into its epilogue."""
+    lib, dev = load(), "cuda"
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    dh = _bf(torch.randn(B, 512, generator=g) * 0.1).to(dev)
+    w1 = _bf(torch.randn(3136, 512, generator=g) * 0.05).to(dev)
+    code = (torch.randint(0, 4, (B, 3136), generator=g) | (torch.randint(0, 2, (B, 3136), generator=g) << 2)).to(torch.uint8).to(dev)
+    dy = torch.full((B, 14, 14, 64), 7.0, dtype=torch.bfloat16, device=dev)      # every element must be overwritten
+    gb = torch.zeros(64, device=dev)
+    check(lib.dm_fc1_dgrad_unpool(ptr(dh), ptr(w1), ptr(code), ptr(dy), ptr(gb), B, stream_ptr()), "fc1_dgrad_unpool")
+    dx = dh.float() @ w1.float().t()                                              # [B,3136] = [B,7,7,64]
+    idx, act = _decode_pool(code)
+    masked = (dx * act).reshape(B, 7, 7, 64)
+    ref = torch.zeros(B, 7, 2, 7, 2, 64, device=dev)
+    idx = idx.reshape(B, 7, 7, 64)
+    for q in range(4):
+        ref[:, :, q >> 1, :, q & 1, :] = masked * (idx == q)
+    ref = ref.reshape(B, 14, 14, 64)
+    scale = dx.abs().max().item()
+    return [("fc1_dgrad_unpool.dy(rel)", (dy.float() - ref).abs().max().item() / scale, 0.01),
+            ("fc1_dgrad_unpool.g_bias(rel)", (gb - masked.sum((0, 1, 2))).abs().max().item() / masked.sum((0, 1, 2)).abs().max().item(), 2e-3)]
 
 
 def _engine(B: int, seed: int = 5):
@@ -228,5 +255,5 @@ def check_mlp2_end_to_end() -> List[Result]:
     return check_mlp_end_to_end("mlp2", B=96, hidden=128, seed=22)
 
 
-ALL_CHECKS = [check_conv1_fwd, check_conv2_fwd, check_conv2_dgrad, check_conv2_wgrad, check_fc2_loss,
+ALL_CHECKS = [check_conv1_fwd, check_conv2_fwd, check_conv2_dgrad, check_conv2_wgrad, check_fc2_loss, check_fc1_dgrad_unpool,
               check_end_to_end, check_training_reduces_loss, check_mlp_end_to_end, check_mlp2_end_to_end]

@@ -26,7 +26,7 @@ import torch
 from ..ops.lib import check, load, require_blackwell, stream_ptr
 from .backends import Backend, StepInfo
 from .context import ReplicaContext
-from .symm_mem import SymmetricBuffer
+from .symm_mem import SymmetricBuffer, allocate_symmetric
 
 
 class FusedBackend(Backend):
@@ -41,6 +41,8 @@ class FusedBackend(Backend):
         # programmatic dependent launch between the kernels of a step (DMNIST_PDL=0 disables)
         self.lib.dm_set_pdl(0 if os.environ.get("DMNIST_PDL", "1") == "0" else 1)
         self.ctas = ctas or int(os.environ.get("DMNIST_SYNC_CTAS", "148"))
+        # NVLS (in-switch reduction + multicast store) for the arenas when the fabric offers it; DMNIST_NVLS=0 -> P2P only
+        self.want_nvls = os.environ.get("DMNIST_NVLS", "1") != "0"
         self.timeout_ms = timeout_ms
         self._buffers: List[SymmetricBuffer] = []
         self._by_ptr: Dict[int, SymmetricBuffer] = {}
@@ -56,7 +58,7 @@ class FusedBackend(Backend):
 
     # ---- memory ---------------------------------------------------------------------------
     def allocate(self, numel: int) -> torch.Tensor:
-        buf = SymmetricBuffer(numel * 4, self.ctx.rank, self.ctx.world_size, self.ctx.device)
+        buf = allocate_symmetric(numel * 4, self.ctx.rank, self.ctx.world_size, self.ctx.device, self.want_nvls)
         self._buffers.append(buf)
         t = buf.view(torch.float32, 0, numel)
         self._by_ptr[t.data_ptr()] = buf
@@ -119,8 +121,13 @@ class FusedBackend(Backend):
             self.ctrl.ptr_table(), pb.ptr_table(), gb.ptr_table(), self.ctx.rank, self.ctx.world_size, int(k),
             ctypes.c_longlong(params.numel()), ctypes.c_float(lr0), ctypes.c_float(decay_rate), int(decay_steps),
             ctypes.c_float(self.drop_keep), ctypes.c_uint(self.drop_seed), ctypes.c_double(self.timeout_ms),
-            ctypes.c_void_p(0 if self.shadow is None else self.shadow.data_ptr()), int(self.ctas), stream_ptr(stream))
+            ctypes.c_void_p(0 if self.shadow is None else self.shadow.data_ptr()), int(self.ctas), stream_ptr(stream),
+            ctypes.c_void_p(gb.multicast_ptr if pb.multicast_ptr else 0), ctypes.c_void_p(pb.multicast_ptr if gb.multicast_ptr else 0))
         check(rc, "dm_fused_sync_sgd")
+
+    @property
+    def nvls_active(self) -> bool:
+        return bool(self._buffers) and all(b.multicast_ptr for b in self._buffers[:2])
 
     def enqueue_straggler_delay(self, prob: float, usec: float, seed: int = 12345,
                                 stream: Optional[torch.cuda.Stream] = None) -> None:

@@ -36,6 +36,11 @@ def test_fc2_softmax_xent_fwd_bwd():
     _run("check_fc2_loss", B=13, seed=13)
 
 
+def test_fc1_dgrad_with_fused_unpool_epilogue():
+    _run("check_fc1_dgrad_unpool")
+    _run("check_fc1_dgrad_unpool", B=37, seed=15)   # partial M tile: rows beyond the batch contribute nothing
+
+
 def test_end_to_end_gradients_match_autograd():
     _run("check_end_to_end")
     _run("check_end_to_end", B=256, seed=14)   # the benchmark batch size

@@ -5,6 +5,15 @@
 set -u
 mkdir -p gpurun_out
 STAGES="${*:-tests bench launches ncu}"
+GPUS="${GPUS:-1}"      # bench stages run on this many GPUs, launched exactly like the driver does (torchrun for N>1)
+run_bench() {          # run_bench <extra args...>
+  if [ "$GPUS" -gt 1 ]; then
+    timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$GPUS" --master-addr 127.0.0.1 --master-port 29517 \
+        bench.py --gpus "$GPUS" "$@"
+  else
+    timeout 300 python bench.py --gpus 1 "$@"
+  fi
+}
 has() { [[ " $STAGES " == *" $1 "* ]]; }
 nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/nvsmi_start.csv 2>&1
 
@@ -18,12 +27,25 @@ if has bench; then
   nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap \
       --format=csv -lms 200 > gpurun_out/clocks.csv 2>&1 &
   SMI=$!
-  timeout 300 python bench.py --gpus 1 --steps 300 --warmup 20 --kernel-times > gpurun_out/bench_ours_1.json 2> gpurun_out/bench_ours_1.err
-  echo "bench ours exit=$?"; cat gpurun_out/bench_ours_1.json; grep KERNEL_TIMES gpurun_out/bench_ours_1.err
-  timeout 300 python bench.py --impl torch_ddp --gpus 1 --steps 300 --warmup 20 > gpurun_out/bench_torch_1.json 2> gpurun_out/bench_torch_1.err
-  echo "bench torch exit=$?"; cat gpurun_out/bench_torch_1.json
+  run_bench --steps 300 --warmup 20 --kernel-times > gpurun_out/bench_ours_$GPUS.json 2> gpurun_out/bench_ours_$GPUS.err
+  echo "bench ours exit=$?"; cat gpurun_out/bench_ours_$GPUS.json; grep KERNEL_TIMES gpurun_out/bench_ours_$GPUS.err; tail -3 gpurun_out/bench_ours_$GPUS.err
+  run_bench --impl torch_ddp --steps 300 --warmup 20 > gpurun_out/bench_torch_$GPUS.json 2> gpurun_out/bench_torch_$GPUS.err
+  echo "bench torch exit=$?"; cat gpurun_out/bench_torch_$GPUS.json
   timeout 300 python bench.py --impl reference --gpus 1 > gpurun_out/bench_ref_1.json 2>&1
   kill $SMI
+fi
+
+if has ab; then
+  # A/B switches: one short bench per entry of $AB (e.g. AB="DMNIST_CONV1_FWD=1 DMNIST_PRIO=0"), ms_per_step only
+  for kv in ${AB:-}; do
+    r=$(env $kv python bench.py --gpus 1 --steps 200 --warmup 10 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['e2e']['ms_per_step'])")
+    echo "AB $kv -> ms_per_step (device, e2e) = $r" | tee -a gpurun_out/ab.txt
+  done
+fi
+
+if has trace; then
+  run_bench --steps 20 --warmup 5 --trace gpurun_out/timeline > gpurun_out/trace_run.log 2>&1
+  echo "trace exit=$?"; cat gpurun_out/timeline.txt
 fi
 
 if has launches; then
