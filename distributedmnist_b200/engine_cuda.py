@@ -92,6 +92,7 @@ class CudaLeNetEngine(ComputeEngine):
         self._wgrad_late = os.environ.get("DMNIST_WGRAD_LATE", "1") != "0"
         self._branches = os.environ.get("DMNIST_BRANCHES", "1") != "0"
         self._fuse_unpool = os.environ.get("DMNIST_FUSE_UNPOOL", "1") != "0"
+        self._conv1_tc = os.environ.get("DMNIST_CONV1_TC", "1") != "0"    # conv1 fwd / wgrad on tcgen05 (csrc/conv1_tc.cu)
         self._copy_done = [torch.cuda.Event() for _ in range(2)]
         self._slot_free = [torch.cuda.Event() for _ in range(2)]
         self._graphs = [None, None]
@@ -153,8 +154,9 @@ class CudaLeNetEngine(ComputeEngine):
     def _launch_forward(self, images: torch.Tensor, labels: torch.Tensor, B: int, train: bool,
                         logits_out: Optional[torch.Tensor] = None) -> int:
         lib, sp, p, pb = self.lib, stream_ptr(), self.p, self.pb
-        check(lib.dm_conv1_fwd(ptr(images), ptr(p["conv1_weights"]), ptr(p["conv1_biases"]), ptr(self.a1),
-                               ptr(self.code1), B, *self._zero_args(train), sp), "conv1_fwd")
+        conv1_fwd = lib.dm_conv1_fwd_tc if self._conv1_tc else lib.dm_conv1_fwd
+        check(conv1_fwd(ptr(images), ptr(p["conv1_weights"]), ptr(p["conv1_biases"]), ptr(self.a1),
+                        ptr(self.code1), B, *self._zero_args(train), sp), "conv1_fwd")
         check(lib.dm_conv2_fwd(ptr(self.a1), ptr(pb["conv2_weights"]), ptr(p["conv2_biases"]), ptr(self.a2),
                                ptr(self.code2), B, sp), "conv2_fwd")
         # fc1: a2[B,3136] (K-major) * W1[3136,512] (MN-major), split-K: 7 partial tiles stored side by side
@@ -216,8 +218,9 @@ class CudaLeNetEngine(ComputeEngine):
                 join2.record(self._side[1])
         if not late:
             check(lib.dm_conv2_dgrad(ptr(self.dy2), ptr(pb["conv2_weights"]), ptr(self.dx1), B, sp), "conv2_dgrad")
-        check(lib.dm_conv1_wgrad(ptr(images), ptr(self.dx1), ptr(self.code1), ptr(g["conv1_weights"]),
-                                 ptr(g["conv1_biases"]), B, sp), "conv1_wgrad")
+        conv1_wgrad = lib.dm_conv1_wgrad_tc if self._conv1_tc else lib.dm_conv1_wgrad
+        check(conv1_wgrad(ptr(images), ptr(self.dx1), ptr(self.code1), ptr(g["conv1_weights"]),
+                          ptr(g["conv1_biases"]), B, sp), "conv1_wgrad")
         if branch:
             main.wait_event(join1)
             main.wait_event(join2)
@@ -249,7 +252,7 @@ class CudaLeNetEngine(ComputeEngine):
             yield "memsets", lambda: self._launch_zero()
             fw = []
             # forward / backward are issued kernel by kernel so an event can sit between any two
-            yield "conv1_fwd", lambda: check(lib.dm_conv1_fwd(ptr(img), ptr(p["conv1_weights"]), ptr(p["conv1_biases"]),
+            yield "conv1_fwd", lambda: check((lib.dm_conv1_fwd_tc if self._conv1_tc else lib.dm_conv1_fwd)(ptr(img), ptr(p["conv1_weights"]), ptr(p["conv1_biases"]),
                                                               ptr(self.a1), ptr(self.code1), B, *self._zero_args(True), sp),
                                              "conv1_fwd")
             yield "conv2_fwd", lambda: check(lib.dm_conv2_fwd(ptr(self.a1), ptr(pb["conv2_weights"]), ptr(p["conv2_biases"]),
@@ -281,7 +284,7 @@ class CudaLeNetEngine(ComputeEngine):
                                                "conv2_wgrad")
             yield "conv2_dgrad", lambda: check(lib.dm_conv2_dgrad(ptr(self.dy2), ptr(pb["conv2_weights"]), ptr(self.dx1), B, sp),
                                                "conv2_dgrad")
-            yield "conv1_wgrad", lambda: check(lib.dm_conv1_wgrad(ptr(img), ptr(self.dx1), ptr(self.code1),
+            yield "conv1_wgrad", lambda: check((lib.dm_conv1_wgrad_tc if self._conv1_tc else lib.dm_conv1_wgrad)(ptr(img), ptr(self.dx1), ptr(self.code1),
                                                                   ptr(g["conv1_weights"]), ptr(g["conv1_biases"]), B, sp),
                                                "conv1_wgrad")
             yield "fused_sync_sgd", lambda: self.backend.enqueue(self.params, self.grads, **self._opt_args)

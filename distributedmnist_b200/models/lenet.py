@@ -80,15 +80,17 @@ def _q(t: torch.Tensor, on: bool) -> torch.Tensor:
 
 def lenet_forward(p: Dict[str, torch.Tensor], images: torch.Tensor, train: bool = True,
                   keep_mask: Optional[torch.Tensor] = None, keep_prob: float = 0.5,
-                  emulate_bf16: bool = False) -> torch.Tensor:
+                  emulate_bf16: bool = False, conv1_bf16: Optional[bool] = None) -> torch.Tensor:
     """Logits ``[B, 10]`` from NHWC fp32 images ``[B, 28, 28, 1]``.
 
-    ``p`` maps parameter names to tensors in TF layout (HWIO / [in, out]).
+    ``p`` maps parameter names to tensors in TF layout (HWIO / [in, out]).  ``conv1_bf16`` (default: same as
+    ``emulate_bf16``) rounds the conv1 operands too -- the tcgen05 conv1 (csrc/conv1_tc.cu) does, the SIMT one does not.
     """
     q = emulate_bf16
-    x = images.permute(0, 3, 1, 2)  # NHWC -> NCHW
-    w1 = p["conv1_weights"].permute(3, 2, 0, 1)  # HWIO -> OIHW
-    y = F.conv2d(x, w1, p["conv1_biases"], padding=2)  # conv1 runs fp32 (K=25, SIMT)
+    q1 = q if conv1_bf16 is None else conv1_bf16
+    x = _q(images.permute(0, 3, 1, 2), q1)  # NHWC -> NCHW
+    w1 = _q(p["conv1_weights"], q1).permute(3, 2, 0, 1)  # HWIO -> OIHW
+    y = F.conv2d(x, w1, p["conv1_biases"], padding=2)
     y = _q(F.max_pool2d(F.relu(y), 2, 2), q)
     w2 = _q(p["conv2_weights"], q).permute(3, 2, 0, 1)
     y = F.conv2d(y, w2, p["conv2_biases"], padding=2)

@@ -36,7 +36,7 @@ def _decode_pool(code: torch.Tensor):
     return (code & 3).long(), ((code >> 2) & 1).bool()
 
 
-def check_conv1_fwd(B: int = 8, seed: int = 0) -> List[Result]:
+def check_conv1_fwd(B: int = 8, seed: int = 0, tc: bool = False) -> List[Result]:
     lib, dev = load(), "cuda"
     g = torch.Generator(device="cpu").manual_seed(seed)
     x = (torch.rand(B, 28, 28, generator=g) - 0.5).to(dev)
@@ -45,8 +45,11 @@ def check_conv1_fwd(B: int = 8, seed: int = 0) -> List[Result]:
     out = torch.zeros(B, 14, 14, 32, dtype=torch.bfloat16, device=dev)
     code = torch.zeros(B, 14, 14, 32, dtype=torch.uint8, device=dev)
     junk = torch.ones(100, device=dev)
-    check(lib.dm_conv1_fwd(ptr(x), ptr(w), ptr(b), ptr(out), ptr(code), B, ptr(junk), 100, ctypes.c_void_p(0), 0,
-                           ctypes.c_void_p(0), 0, stream_ptr()), "conv1_fwd")
+    fn = lib.dm_conv1_fwd_tc if tc else lib.dm_conv1_fwd
+    check(fn(ptr(x), ptr(w), ptr(b), ptr(out), ptr(code), B, ptr(junk), 100, ctypes.c_void_p(0), 0,
+             ctypes.c_void_p(0), 0, stream_ptr()), "conv1_fwd")
+    if tc:   # the tensor-core path rounds its operands to bf16: compare against the same rounding
+        x, w = x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float()
     conv = F.conv2d(x[:, None], w.permute(3, 2, 0, 1), b, padding=2)
     ref = _nhwc(F.max_pool2d(F.relu(conv), 2, 2))
     err = (out.float() - ref).abs().max().item()
@@ -55,9 +58,44 @@ def check_conv1_fwd(B: int = 8, seed: int = 0) -> List[Result]:
     win = _nhwc(conv).reshape(B, 14, 2, 14, 2, 32).permute(0, 1, 3, 5, 2, 4).reshape(B, 14, 14, 32, 4)
     sel = torch.gather(win, 4, idx[..., None])[..., 0]
     err_idx = (sel - win.max(dim=4).values).abs().max().item()
-    err_act = ((sel > 0) != act).float().sum().item()
-    return [("conv1_fwd.out", err, 0.02), ("conv1_fwd.argmax", err_idx, 1e-5), ("conv1_fwd.relu_flag", err_act, 0.5),
-            ("conv1_fwd.zeroing", junk.abs().max().item(), 1e-12)]
+    bad_act = ((sel > 1e-4) & ~act) | ((sel < -1e-4) & act)
+    tag = "conv1_fwd_tc" if tc else "conv1_fwd"
+    return [(tag + ".out", err, 0.02), (tag + ".argmax", err_idx, 1e-4 if tc else 1e-5),
+            (tag + ".relu_flag", bad_act.float().sum().item(), 0.5), (tag + ".zeroing", junk.abs().max().item(), 1e-12)]
+
+
+def check_conv1_fwd_tc(B: int = 8, seed: int = 0) -> List[Result]:
+    return check_conv1_fwd(B, seed, tc=True)
+
+
+def check_conv1_wgrad(B: int = 8, seed: int = 7, tc: bool = True) -> List[Result]:
+    """conv1 weight/bias gradient fused with the maxpool1/ReLU1 backward (SIMT and tcgen05 versions)."""
+    lib, dev = load(), "cuda"
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = (torch.rand(B, 28, 28, generator=g) - 0.5).to(dev)
+    dpool = _bf(torch.randn(B, 14, 14, 32, generator=g) * 0.1).to(dev)
+    code = (torch.randint(0, 4, (B, 14, 14, 32), generator=g) | (torch.randint(0, 2, (B, 14, 14, 32), generator=g) << 2)) \
+        .to(torch.uint8).to(dev)
+    gw = torch.zeros(25, 32, device=dev)
+    gb = torch.zeros(32, device=dev)
+    fn = lib.dm_conv1_wgrad_tc if tc else lib.dm_conv1_wgrad
+    check(fn(ptr(x), ptr(dpool), ptr(code), ptr(gw), ptr(gb), B, stream_ptr()), "conv1_wgrad")
+    idx, act = _decode_pool(code)
+    masked = dpool.float() * act
+    dy = torch.zeros(B, 14, 2, 14, 2, 32, device=dev)
+    for q in range(4):
+        dy[:, :, q >> 1, :, q & 1, :] = masked * (idx == q)
+    dy = dy.reshape(B, 28, 28, 32)
+    xr = x.to(torch.bfloat16).float() if tc else x
+    ref = torch.nn.grad.conv2d_weight(xr[:, None], (32, 1, 5, 5), _nchw(dy), padding=2)    # [32,1,5,5]
+    ref = ref[:, 0].permute(1, 2, 0).reshape(25, 32)
+    tag = "conv1_wgrad_tc" if tc else "conv1_wgrad"
+    return [(tag + ".g_w(rel)", (gw - ref).abs().max().item() / ref.abs().max().item(), 2e-3),
+            (tag + ".g_b(rel)", (gb - masked.sum((0, 1, 2))).abs().max().item() / masked.sum((0, 1, 2)).abs().max().item(), 2e-3)]
+
+
+def check_conv1_wgrad_simt(B: int = 8, seed: int = 7) -> List[Result]:
+    return check_conv1_wgrad(B, seed, tc=False)
 
 
 def check_conv2_fwd(B: int = 8, seed: int = 1) -> List[Result]:
@@ -187,7 +225,8 @@ def check_end_to_end(B: int = 64, seed: int = 5) -> List[Result]:
     # reference on the same weights
     flat = eng.params.detach().clone().requires_grad_(True)
     mask = dropout_keep_mask(dropout_seed_mix(seed, 0, 0), B, 512, 0.5, device="cuda")
-    logits = lenet_forward(spec.views(flat), x.cuda(), train=True, keep_mask=mask, emulate_bf16=True)
+    logits = lenet_forward(spec.views(flat), x.cuda(), train=True, keep_mask=mask, emulate_bf16=True,
+                           conv1_bf16=eng._conv1_tc)
     rloss, racc = loss_and_accuracy(logits, y.cuda())
     rloss.backward()
     out: List[Result] = [("e2e.loss", abs(loss - rloss.item()), 0.02 * max(1.0, abs(rloss.item()))),
@@ -255,5 +294,5 @@ def check_mlp2_end_to_end() -> List[Result]:
     return check_mlp_end_to_end("mlp2", B=96, hidden=128, seed=22)
 
 
-ALL_CHECKS = [check_conv1_fwd, check_conv2_fwd, check_conv2_dgrad, check_conv2_wgrad, check_fc2_loss, check_fc1_dgrad_unpool,
+ALL_CHECKS = [check_conv1_fwd, check_conv1_fwd_tc, check_conv1_wgrad, check_conv1_wgrad_simt, check_conv2_fwd, check_conv2_dgrad, check_conv2_wgrad, check_fc2_loss, check_fc1_dgrad_unpool,
               check_end_to_end, check_training_reduces_loss, check_mlp_end_to_end, check_mlp2_end_to_end]

@@ -16,6 +16,18 @@ def test_conv1_fwd_fused_bias_relu_pool():
     _run("check_conv1_fwd", B=3, seed=9)       # batch not a multiple of anything
 
 
+def test_conv1_fwd_tcgen05_software_im2col():
+    _run("check_conv1_fwd_tc")
+    _run("check_conv1_fwd_tc", B=3, seed=9)        # one partial tile
+    _run("check_conv1_fwd_tc", B=150, seed=19)     # 230 tiles > 148 CTAs: two-stage operand ring + TMEM double buffering
+
+
+def test_conv1_wgrad_tcgen05_and_simt():
+    _run("check_conv1_wgrad")
+    _run("check_conv1_wgrad", B=150, seed=20)
+    _run("check_conv1_wgrad_simt")
+
+
 def test_conv2_fwd_tcgen05_implicit_gemm():
     _run("check_conv2_fwd")
     _run("check_conv2_fwd", B=75, seed=10)     # 150 tiles > 148 CTAs: persistent loop + TMEM double buffering

@@ -17,6 +17,17 @@ run_bench() {          # run_bench <extra args...>
 has() { [[ " $STAGES " == *" $1 "* ]]; }
 nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/nvsmi_start.csv 2>&1
 
+if has diag; then
+  # numerics of the newest kernels first; a failing (or hanging: watchdog trap / timeout) tensor-core conv1 falls back to
+  # the SIMT kernels for the rest of the call so the other measurements stay meaningful
+  timeout 180 python tools/gpu_diag_lenet.py ${DIAG:-conv1 fc1_dgrad} > gpurun_out/diag.log 2>&1
+  echo "diag exit=$?"; grep -E "FAIL|EXCEPTION|Error|error" gpurun_out/diag.log | head -20; grep -c " ok" gpurun_out/diag.log
+  if grep -qE "conv1_(fwd|wgrad)_tc.*FAIL|check_conv1.*EXCEPTION|Traceback" gpurun_out/diag.log || ! grep -q "conv1_wgrad_tc" gpurun_out/diag.log; then
+    echo "conv1 tensor-core kernels NOT healthy -> DMNIST_CONV1_TC=0 for the rest of this call"
+    export DMNIST_CONV1_TC=0
+  fi
+fi
+
 if has tests; then
   timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
   echo "pytest exit=$?" >> gpurun_out/pytest_gpu.log
@@ -46,6 +57,18 @@ fi
 if has trace; then
   run_bench --steps 20 --warmup 5 --trace gpurun_out/timeline > gpurun_out/trace_run.log 2>&1
   echo "trace exit=$?"; cat gpurun_out/timeline.txt
+fi
+
+if has sweep; then
+  DM_SWEEP_MAX=${DM_SWEEP_MAX:-67108864} timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$GPUS" \
+      --master-addr 127.0.0.1 --master-port 29519 tools/allreduce_sweep.py > gpurun_out/sweep_$GPUS.log 2>&1
+  echo "sweep exit=$?"; tail -2 gpurun_out/sweep_$GPUS.log | cut -c1-2500
+fi
+
+if has nvlsab; then
+  # same bench with NVLS off (P2P reduce / push): what the in-switch reduction buys
+  DMNIST_NVLS=0 run_bench --steps 300 --warmup 20 > gpurun_out/bench_ours_${GPUS}_p2p.json 2> gpurun_out/bench_ours_${GPUS}_p2p.err
+  echo "bench ours P2P exit=$?"; cat gpurun_out/bench_ours_${GPUS}_p2p.json
 fi
 
 if has launches; then
