@@ -24,7 +24,8 @@
 
 namespace dm {
 
-constexpr int C1T_THREADS = 160;          // warp 0: MMA issuer + TMEM owner, warps 1-4: operand builders / epilogue
+constexpr int C1T_FW_THREADS = 416;       // warp 0: MMA issuer + TMEM owner, warps 1-8: operand builders, warps 9-12: epilogue
+constexpr int C1T_WG_THREADS = 288;       // warp 0: MMA issuer + TMEM owner, warps 1-8: operand builders (warp 4: epilogue)
 constexpr int C1T_TILE = 128;             // pooled pixels per tile
 constexpr int C1T_AP_BYTES = 128 * 64;    // one A_p (or G_p) tile: 128 rows x 32 bf16
 
@@ -54,16 +55,18 @@ DMNIST_DEVICE void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
                : "memory");
 }
 
-// Build the four im2col rows of pooled pixel P (thread = row m of the tile) into A_0..A_3 (8 KB apart).
-DMNIST_DEVICE void build_im2col_rows(uint8_t* a_tiles, int m, long long P, long long total, const float* __restrict__ images) {
-  float patch[6][6];
+// Build two of the four im2col rows of pooled pixel P (thread = row m of the tile): window positions p = 2h, 2h+1
+// (conv row 2ph + h) into A_{2h}, A_{2h+1}.  Two threads share a pooled pixel, one per h, so a tile has 256 builders.
+DMNIST_DEVICE void build_im2col_half(uint8_t* a_tiles, int m, int h, long long P, long long total,
+                                     const float* __restrict__ images) {
+  float patch[5][6];                                  // input rows 2ph-2+h .. 2ph+2+h, columns 2pw-2 .. 2pw+3
   if (P < total) {
     const int b = (int)(P / 196), pos = (int)(P - (long long)b * 196);
     const int ph = pos / 14, pw = pos - ph * 14;
     const float* img = images + (size_t)b * 784;
 #pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      const int y = 2 * ph - 2 + r;
+    for (int r = 0; r < 5; ++r) {
+      const int y = 2 * ph - 2 + h + r;
 #pragma unroll
       for (int c2 = 0; c2 < 3; ++c2) {
         const int x = 2 * pw - 2 + 2 * c2;           // even: the pair (x, x+1) is inside or outside as a whole
@@ -75,23 +78,22 @@ DMNIST_DEVICE void build_im2col_rows(uint8_t* a_tiles, int m, long long P, long 
     }
   } else {
 #pragma unroll
-    for (int r = 0; r < 6; ++r)
+    for (int r = 0; r < 5; ++r)
 #pragma unroll
       for (int c = 0; c < 6; ++c) patch[r][c] = 0.f;
   }
   const float one = P < total ? 1.f : 0.f;
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    const int py = p >> 1, px = p & 1;
+  for (int px = 0; px < 2; ++px) {
     uint32_t w[16];                                   // 32 taps as bf16 pairs
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int t0 = 2 * j, t1 = 2 * j + 1;
-      const float v0 = t0 < 25 ? patch[py + t0 / 5][px + t0 % 5] : (t0 == 25 ? one : 0.f);
-      const float v1 = t1 < 25 ? patch[py + t1 / 5][px + t1 % 5] : (t1 == 25 ? one : 0.f);
+      const float v0 = t0 < 25 ? patch[t0 / 5][px + t0 % 5] : (t0 == 25 ? one : 0.f);
+      const float v1 = t1 < 25 ? patch[t1 / 5][px + t1 % 5] : (t1 == 25 ? one : 0.f);
       w[j] = pack_bf16x2(v0, v1);
     }
-    uint8_t* tile = a_tiles + p * C1T_AP_BYTES;
+    uint8_t* tile = a_tiles + (2 * h + px) * C1T_AP_BYTES;
 #pragma unroll
     for (int c = 0; c < 4; ++c) sts128(tile + swz64(m, c), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
   }
@@ -108,7 +110,7 @@ struct C1FwSmem {
   static constexpr int TOTAL = BIAS_OFF + 128 + 1024;
 };
 
-__global__ void __launch_bounds__(C1T_THREADS, 1)
+__global__ void __launch_bounds__(C1T_FW_THREADS, 1)
 conv1_fwd_tc_kernel(const float* __restrict__ images,   // [B,28,28] fp32
                     const float* __restrict__ w,        // [25][32] fp32
                     const float* __restrict__ bias,     // [32]
@@ -118,22 +120,25 @@ conv1_fwd_tc_kernel(const float* __restrict__ images,   // [B,28,28] fp32
                     int num_tiles, ZeroRanges3 zr) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + C1FwSmem::BAR_OFF);   // [2] 128 arrivals each
-  uint64_t* acc_full = a_full + 2;                                           // [2]
-  uint64_t* acc_empty = acc_full + 2;                                        // [2] 4 arrivals each
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + C1FwSmem::BAR_OFF);   // [2] 256 arrivals each (builders)
+  uint64_t* a_empty = a_full + 2;                                            // [2] tcgen05.commit
+  uint64_t* acc_full = a_empty + 2;                                          // [2] tcgen05.commit
+  uint64_t* acc_empty = acc_full + 2;                                        // [2] 4 arrivals each (epilogue warps)
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* s_bias = reinterpret_cast<float*>(smem + C1FwSmem::BIAS_OFF);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 128); mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&a_full[s], 256); mbar_init(&a_empty[s], 1); mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4);
+    }
     fence_mbar_init();
   }
   if (warp == 0) {
     tmem_alloc<256>(tmem_holder);
     s_bias[lane] = __ldg(bias + lane);
   }
-  if (warp >= 1) {
+  if (warp >= 1 && warp <= 4) {
     // weights: fp32 [25][32] -> bf16 rows of 64 B (k-row = tap), rows 25-31 zero.  128 threads x one 16-byte chunk.
     const int t = threadIdx.x - 32, k = t >> 2, c = t & 3;
     uint32_t pk[4] = {0u, 0u, 0u, 0u};
@@ -152,14 +157,15 @@ conv1_fwd_tc_kernel(const float* __restrict__ images,   // [B,28,28] fp32
   pdl_wait();
   // first kernel of a training step: clear the atomically accumulated gradient regions and the loss accumulator
   {
-    const int gi = blockIdx.x * C1T_THREADS + threadIdx.x;
+    const int gi = blockIdx.x * C1T_FW_THREADS + threadIdx.x;
 #pragma unroll
     for (int r = 0; r < 3; ++r)
       if (zr.ptr[r] != nullptr)
-        for (int i = gi; i < zr.n[r]; i += gridDim.x * C1T_THREADS) zr.ptr[r][i] = 0.f;
+        for (int i = gi; i < zr.n[r]; i += gridDim.x * C1T_FW_THREADS) zr.ptr[r][i] = 0.f;
   }
 
   if (warp == 0) {
+    // ------------------------------ MMA issuer ------------------------------------------------------------
     constexpr uint32_t idesc = make_idesc_bf16(128, 32, /*A MN*/ false, /*B MN*/ true);
     int i = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
@@ -176,29 +182,29 @@ conv1_fwd_tc_kernel(const float* __restrict__ images,   // [B,28,28] fp32
           for (int k = 0; k < 2; ++k)     // K = 32 taps = 2 x UMMA_K: A advances 32 B inside the row, W 16 k-rows = 1024 B
             umma_bf16(tmem_base + s * 128 + p * 32, da0 + (uint64_t)((32 * k) >> 4), db0 + (uint64_t)((1024 * k) >> 4), idesc, k);
         }
+        umma_commit(&a_empty[s]);       // operand stage reusable once these MMAs retire
         umma_commit(&acc_full[s]);
       }
       __syncwarp();
     }
-  } else {
-    const int q = warp & 3;                         // TMEM lane quarter of this warp
-    const int m = q * 32 + lane;                    // tile row = accumulator lane
-    int first = blockIdx.x;
-    if (first < num_tiles) {
-      build_im2col_rows(smem + C1FwSmem::A_OFF, m, (long long)first * C1T_TILE + m, total, images);
-      fence_proxy_async_smem();
-      mbar_arrive(&a_full[0]);
-    }
+  } else if (warp <= 8) {
+    // ------------------------------ operand builders (generic proxy -> fence -> mbarrier) ----------------------
+    const int h = (warp - 1) >> 2, m = ((warp - 1) & 3) * 32 + lane;
     int i = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
       const int s = i & 1;
-      const int tn = t + gridDim.x;
-      if (tn < num_tiles) {
-        // stage s^1 was last read by the MMAs of tile i-1, whose completion this warp observed in the previous epilogue
-        build_im2col_rows(smem + C1FwSmem::A_OFF + (s ^ 1) * 4 * C1T_AP_BYTES, m, (long long)tn * C1T_TILE + m, total, images);
-        fence_proxy_async_smem();
-        mbar_arrive(&a_full[s ^ 1]);
-      }
+      mbar_wait_wd(&a_empty[s], ((i >> 1) & 1) ^ 1);
+      build_im2col_half(smem + C1FwSmem::A_OFF + s * 4 * C1T_AP_BYTES, m, h, (long long)t * C1T_TILE + m, total, images);
+      fence_proxy_async_smem();
+      mbar_arrive(&a_full[s]);
+    }
+  } else {
+    // ------------------------------ epilogue: max-pool in registers, bias, ReLU, argmax code ----------------------
+    const int q = warp & 3;                         // TMEM lane quarter of this warp
+    const int m = q * 32 + lane;                    // tile row = accumulator lane
+    int i = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
+      const int s = i & 1;
       mbar_wait_wd(&acc_full[s], (i >> 1) & 1);
       tc_fence_after_sync();
       const long long P = (long long)t * C1T_TILE + m;
@@ -249,7 +255,7 @@ struct C1WgSmem {
   static constexpr int TOTAL = BAR_OFF + 128 + 1024;
 };
 
-__global__ void __launch_bounds__(C1T_THREADS, 1)
+__global__ void __launch_bounds__(C1T_WG_THREADS, 1)
 conv1_wgrad_tc_kernel(const float* __restrict__ images,          // [B,28,28]
                       const __nv_bfloat16* __restrict__ dpool,   // [B,14,14,32] gradient w.r.t. the pooled activations
                       const uint8_t* __restrict__ code,          // [B,14,14,32]
@@ -258,7 +264,7 @@ conv1_wgrad_tc_kernel(const float* __restrict__ images,          // [B,28,28]
                       long long total, int num_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C1WgSmem::BAR_OFF);   // [2] 128 arrivals
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C1WgSmem::BAR_OFF);   // [2] 256 arrivals
   uint64_t* empty = full + 2;                                              // [2] 1 arrival (tcgen05.commit)
   uint64_t* acc_full = empty + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_full + 1);
@@ -269,7 +275,7 @@ conv1_wgrad_tc_kernel(const float* __restrict__ images,          // [B,28,28]
   const int nt = t_end - t_begin;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&full[s], 256); mbar_init(&empty[s], 1); }
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
@@ -305,8 +311,7 @@ conv1_wgrad_tc_kernel(const float* __restrict__ images,          // [B,28,28]
       __syncwarp();
     }
   } else {
-    const int q = warp & 3;
-    const int m = q * 32 + lane;
+    const int h = (warp - 1) >> 2, m = ((warp - 1) & 3) * 32 + lane;   // two builders per pooled pixel: window rows h = 0, 1
     for (int i = 0; i < nt; ++i) {
       const int s = i & 1;
       uint8_t* stage = smem + s * C1WgSmem::STAGE_BYTES;
@@ -323,16 +328,17 @@ conv1_wgrad_tc_kernel(const float* __restrict__ images,          // [B,28,28]
         cq[1] = __ldg(cp + 1);
       }
       mbar_wait_wd(&empty[s], ((i >> 1) & 1) ^ 1);
-      build_im2col_rows(stage, m, P, total, images);
+      build_im2col_half(stage, m, h, P, total, images);
       const uint32_t g32[16] = {gq[0].x, gq[0].y, gq[0].z, gq[0].w, gq[1].x, gq[1].y, gq[1].z, gq[1].w,
                                 gq[2].x, gq[2].y, gq[2].z, gq[2].w, gq[3].x, gq[3].y, gq[3].z, gq[3].w};
       const uint32_t cw[8] = {cq[0].x, cq[0].y, cq[0].z, cq[0].w, cq[1].x, cq[1].y, cq[1].z, cq[1].w};
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
+      for (int px = 0; px < 2; ++px) {
+        const uint32_t p = 2u * (uint32_t)h + (uint32_t)px;
         uint32_t o[16];
 #pragma unroll
         for (int w8 = 0; w8 < 8; ++w8) {     // same byte-parallel mask as the unpool epilogue of gemm_tc.cu
-          const uint32_t xz = (cw[w8] & 0x07070707u) ^ (0x04040404u | (0x01010101u * (uint32_t)p));
+          const uint32_t xz = (cw[w8] & 0x07070707u) ^ (0x04040404u | (0x01010101u * p));
           const uint32_t hit = ~(xz + 0x7f7f7f7fu) & 0x80808080u;
           o[2 * w8] = g32[2 * w8] & prmt(hit, 0u, 0x9988u);
           o[2 * w8 + 1] = g32[2 * w8 + 1] & prmt(hit, 0u, 0xbbaau);
@@ -344,7 +350,7 @@ conv1_wgrad_tc_kernel(const float* __restrict__ images,          // [B,28,28]
       fence_proxy_async_smem();
       mbar_arrive(&full[s]);
     }
-    if (nt > 0 && q == 0) {
+    if (nt > 0 && warp == 4) {
       // accumulator rows 0-31 = taps (25 = bias); this warp owns TMEM lanes 0-31
       mbar_wait_wd(acc_full, 0);
       tc_fence_after_sync();
@@ -384,7 +390,7 @@ int dm_conv1_fwd_tc(const void* images, const void* w, const void* bias, void* o
   const long long total = (long long)B * 196;
   const int tiles = (int)((total + C1T_TILE - 1) / C1T_TILE);
   const int grid = tiles < 148 ? tiles : 148;
-  return (int)launch_kernel(conv1_fwd_tc_kernel, dim3(grid), dim3(C1T_THREADS), C1FwSmem::TOTAL,
+  return (int)launch_kernel(conv1_fwd_tc_kernel, dim3(grid), dim3(C1T_FW_THREADS), C1FwSmem::TOTAL,
                             reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const float*>(images),
                             reinterpret_cast<const float*>(w), reinterpret_cast<const float*>(bias),
                             reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<uint8_t*>(code), total, tiles, zr);
@@ -400,8 +406,8 @@ int dm_conv1_wgrad_tc(const void* images, const void* dpool, const void* code, v
   }
   const long long total = (long long)B * 196;
   const int tiles = (int)((total + C1T_TILE - 1) / C1T_TILE);
-  const int grid = tiles < 148 ? tiles : 148;
-  return (int)launch_kernel(conv1_wgrad_tc_kernel, dim3(grid), dim3(C1T_THREADS), C1WgSmem::TOTAL,
+  const int grid = tiles < g_max_ctas ? tiles : g_max_ctas;
+  return (int)launch_kernel(conv1_wgrad_tc_kernel, dim3(grid), dim3(C1T_WG_THREADS), C1WgSmem::TOTAL,
                             reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const float*>(images),
                             reinterpret_cast<const __nv_bfloat16*>(dpool), reinterpret_cast<const uint8_t*>(code),
                             reinterpret_cast<float*>(g_w), reinterpret_cast<float*>(g_b), total, tiles);

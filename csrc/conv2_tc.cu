@@ -468,7 +468,7 @@ int dm_conv2_dgrad_dbg(const void* dy, const void* w_bf16, void* dx, int B, void
     configured = true;
   }
   const int tiles = 2 * B;
-  const int grid = tiles < 148 ? tiles : 148;
+  const int grid = tiles < g_max_ctas ? tiles : g_max_ctas;
   return (int)launch_kernel(conv2_dgrad_kernel, dim3(grid), dim3(CV_THREADS), DgSmem::TOTAL,
                             reinterpret_cast<cudaStream_t>(stream), tmDY, tmW, reinterpret_cast<__nv_bfloat16*>(dx), tiles,
                             reinterpret_cast<unsigned long long*>(dbg));
@@ -486,7 +486,7 @@ int dm_conv2_wgrad(const void* a1, const void* dy, void* g_w, int B, void* strea
     configured = true;
   }
   const int tiles = 2 * B;
-  int splits = 148 / WG_GROUPS;   // 21 -> 147 CTAs
+  int splits = g_max_ctas / WG_GROUPS;   // 148 SMs: 21 -> 147 CTAs
   if (splits > tiles) splits = tiles;
   return (int)launch_kernel(conv2_wgrad_kernel, dim3(WG_GROUPS * splits), dim3(CV_THREADS), WgSmem::TOTAL,
                             reinterpret_cast<cudaStream_t>(stream), tmX, tmDY, reinterpret_cast<float*>(g_w), tiles, splits);

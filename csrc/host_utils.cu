@@ -7,6 +7,7 @@
 namespace dm {
 
 int g_pdl = 0;
+int g_max_ctas = 148;
 
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -87,6 +88,11 @@ int make_tmap_nhwc_bf16(CUtensorMap* out, const void* base, int C, int W, int H,
 }  // namespace dm
 
 extern "C" int dm_version() { return 2; }
+
+extern "C" int dm_set_max_ctas(int n) {
+  dm::g_max_ctas = (n >= 8 && n <= 148) ? n : 148;
+  return dm::g_max_ctas;
+}
 
 extern "C" int dm_set_pdl(int on) {
   dm::g_pdl = on ? 1 : 0;

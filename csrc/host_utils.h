@@ -26,6 +26,9 @@ namespace dm {
 // set up while the previous kernel drains -- the ~2-3 us launch gap between the step's 11 dependent
 // kernels disappears (also inside a captured CUDA graph: the edges become programmatic).
 extern int g_pdl;
+// Upper bound for the persistent kernels' grids (default 148 = one CTA per SM).  The bucketed aggregation lowers it
+// for the backward kernels that run next to the early sync kernel, so those leave SMs free for it.
+extern int g_max_ctas;
 
 template <typename Kern, typename... Args>
 inline cudaError_t launch_kernel(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {

@@ -102,6 +102,8 @@ class CudaLeNetEngine(ComputeEngine):
         p_fc1 = self.spec.param("fc1_weights")
         self._zero_ranges = [(0, p_fc1.offset), (p_fc1.offset + p_fc1.numel, self.spec.arena_numel)]
         self._seed_mix0 = dropout_seed_mix(seed, 0, rank)
+        self._bucket_split = p_fc1.offset          # [0, split) = conv parameters (late bucket), [split, end) = fc (early)
+        self._bucketed = False
         self._epoch_ptr = ctypes.c_void_p(backend.ctrl.local_ptr + backend._off["epoch"])
         self.launches_per_step = 0
 
@@ -145,6 +147,13 @@ class CudaLeNetEngine(ComputeEngine):
         self._straggler = getattr(opt, "_straggler", None)
         self._stamp = getattr(opt, "mode", "") == "cdf"
         self._graphs = [None, None]
+        # Bucketed aggregation (csrc/fused_sync.cu): full participation on more than one replica.  The fc bucket (96.9 % of
+        # the bytes) is exchanged by a 20-CTA kernel NEXT TO conv2 dgrad/wgrad + conv1 wgrad, which are capped at 128 CTAs.
+        n = self.backend.ctx.world_size
+        self._bucketed = (hasattr(self, "_bucket_split") and n > 1 and int(k) == n and self._branches
+                          and self.backend.drop_keep <= 0.0 and os.environ.get("DMNIST_BUCKET", "1") != "0")
+        self._early_ctas = int(os.environ.get("DMNIST_EARLY_CTAS", "20"))
+        self.lib.dm_set_max_ctas(148 - self._early_ctas if self._bucketed else 148)
 
     def params_updated(self) -> None:
         """Parameters were written from the host (init / restore): refresh the bf16 shadow."""
@@ -171,7 +180,7 @@ class CudaLeNetEngine(ComputeEngine):
                                  ctypes.c_float(self.keep_prob), sp), "fc2_fwd_bwd")
         return 4
 
-    def _launch_backward(self, images: torch.Tensor, B: int) -> int:
+    def _launch_backward(self, images: torch.Tensor, B: int, early_sync: bool = False) -> int:
         """Backward as a small DAG: the two weight-gradient GEMMs have no consumer before the aggregation
         kernel, so they run on side streams (captured as parallel graph branches) next to the data-gradient
         chain fc1_dgrad -> unpool2 -> conv2_dgrad -> conv1_wgrad."""
@@ -189,7 +198,7 @@ class CudaLeNetEngine(ComputeEngine):
             # fc2 weight/bias + fc1 bias gradients: only the aggregation kernel consumes them
             check(lib.dm_fc2_wgrad(ptr(self.h_act), ptr(self.dlogits), ptr(self.dh), ptr(g["fc2_weights"]),
                                    ptr(g["fc2_biases"]), ptr(g["fc1_biases"]), B, stream_ptr()), "fc2_wgrad")
-            if branch:
+            if branch and not early_sync:
                 join1 = torch.cuda.Event()
                 join1.record(self._side[0])
         sp = stream_ptr()
@@ -202,6 +211,21 @@ class CudaLeNetEngine(ComputeEngine):
             G.gemm_bf16_raw(self.dh, pb["fc1_weights"], self.dxfc, B, 3136, 512, 512, 512, 3136, False, False,
                             G.EPI_STORE_BF16, bn=64)
             check(lib.dm_unpool2(ptr(self.dxfc), ptr(self.code2), ptr(self.dy2), ptr(g["conv2_biases"]), B, sp), "unpool2")
+        if early_sync:
+            # early bucket: every fc gradient is final once fc1_wgrad / fc2_wgrad are done; the kernel also rewrites my
+            # shard of the fc1 bf16 shadow, which fc1_dgrad (just launched on the main stream) still reads -> order after it
+            ev_du = torch.cuda.Event()
+            ev_du.record(main)
+            with torch.cuda.stream(self._side[0]):
+                self._side[0].wait_event(ev_du)
+                if self._straggler is not None:
+                    self.backend.enqueue_straggler_delay(self._straggler.prob, self._straggler.usec, stream=self._side[0])
+                oa = self._opt_args
+                self.backend.enqueue_bucket(self.params, self.grads, 1, self._bucket_split, self.spec.arena_numel,
+                                            self._bucket_split, self.spec.arena_numel, oa["lr0"], oa["decay_rate"],
+                                            oa["decay_steps"], ctas=self._early_ctas, stream=self._side[0])
+                join1 = torch.cuda.Event()
+                join1.record(self._side[0])
         late = branch and self._wgrad_late
         if late:
             # conv2 dgrad and wgrad each fill the machine (1 CTA/SM, ~200 KB smem): side by side they only slow the chain
@@ -314,8 +338,14 @@ class CudaLeNetEngine(ComputeEngine):
             n += 1
         n += self._launch_zero()
         n += self._launch_forward(self.images[slot], self.labels[slot], self.batch_size, True)
-        n += self._launch_backward(self.images[slot], self.batch_size)
-        if with_sync:
+        bucketed = with_sync and self._bucketed
+        n += self._launch_backward(self.images[slot], self.batch_size, early_sync=bucketed)
+        if bucketed:
+            oa = self._opt_args
+            self.backend.enqueue_bucket(self.params, self.grads, 2, 0, self._bucket_split, self._bucket_split,
+                                        self.spec.arena_numel, oa["lr0"], oa["decay_rate"], oa["decay_steps"])
+            n += 2 + (1 if self._straggler is not None else 0)
+        elif with_sync:
             if self._straggler is not None:
                 self.backend.enqueue_straggler_delay(self._straggler.prob, self._straggler.usec)
                 n += 1

@@ -42,7 +42,11 @@ class FusedBackend(Backend):
         self.lib.dm_set_pdl(0 if os.environ.get("DMNIST_PDL", "1") == "0" else 1)
         self.ctas = ctas or int(os.environ.get("DMNIST_SYNC_CTAS", "148"))
         # NVLS (in-switch reduction + multicast store) for the arenas when the fabric offers it; DMNIST_NVLS=0 -> P2P only
-        self.want_nvls = os.environ.get("DMNIST_NVLS", "1") != "0"
+        #   DMNIST_NVLS unset: allocate multicast-capable arenas, use multimem from 4 replicas up (at 2 the peer path is
+        #   faster: measured 106 vs 115 us/step, profiles/bench_r1_call23_2gpu.txt); =1 always; =0 never (CUDA-IPC arenas)
+        nv = os.environ.get("DMNIST_NVLS", "")
+        self.want_nvls = nv != "0"
+        self.use_nvls = nv == "1" or (nv == "" and ctx.world_size >= 4)
         self.timeout_ms = timeout_ms
         self._buffers: List[SymmetricBuffer] = []
         self._by_ptr: Dict[int, SymmetricBuffer] = {}
@@ -122,12 +126,30 @@ class FusedBackend(Backend):
             ctypes.c_longlong(params.numel()), ctypes.c_float(lr0), ctypes.c_float(decay_rate), int(decay_steps),
             ctypes.c_float(self.drop_keep), ctypes.c_uint(self.drop_seed), ctypes.c_double(self.timeout_ms),
             ctypes.c_void_p(0 if self.shadow is None else self.shadow.data_ptr()), int(self.ctas), stream_ptr(stream),
-            ctypes.c_void_p(gb.multicast_ptr if pb.multicast_ptr else 0), ctypes.c_void_p(pb.multicast_ptr if gb.multicast_ptr else 0))
+            *self._mc_ptrs(pb, gb))
         check(rc, "dm_fused_sync_sgd")
+
+    def _mc_ptrs(self, pb, gb):
+        on = self.use_nvls and pb.multicast_ptr and gb.multicast_ptr
+        return ctypes.c_void_p(gb.multicast_ptr if on else 0), ctypes.c_void_p(pb.multicast_ptr if on else 0)
+
+    def enqueue_bucket(self, params: torch.Tensor, grads: torch.Tensor, phase: int, begin: int, end: int,
+                       early_begin: int, early_end: int, lr0: float, decay_rate: float = 1.0, decay_steps: int = 1,
+                       ctas: int = 0, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Bucketed aggregation (K == N, world_size > 1): ``phase`` 1 = early bucket ``[begin, end)`` (floats) on a few
+        CTAs next to the remaining backward kernels, 2 = late bucket + completion of the step (csrc/fused_sync.cu)."""
+        pb, gb = self._by_ptr[params.data_ptr()], self._by_ptr[grads.data_ptr()]
+        rc = self.lib.dm_fused_sync_bucket(
+            self.ctrl.ptr_table(), pb.ptr_table(), gb.ptr_table(), self.ctx.rank, self.ctx.world_size, int(phase),
+            ctypes.c_longlong(begin), ctypes.c_longlong(end), ctypes.c_longlong(early_begin), ctypes.c_longlong(early_end),
+            ctypes.c_float(lr0), ctypes.c_float(decay_rate), int(decay_steps), ctypes.c_double(self.timeout_ms),
+            ctypes.c_void_p(0 if self.shadow is None else self.shadow.data_ptr()), int(ctas), stream_ptr(stream),
+            *self._mc_ptrs(pb, gb))
+        check(rc, "dm_fused_sync_bucket")
 
     @property
     def nvls_active(self) -> bool:
-        return bool(self._buffers) and all(b.multicast_ptr for b in self._buffers[:2])
+        return self.use_nvls and bool(self._buffers) and all(b.multicast_ptr for b in self._buffers[:2])
 
     def enqueue_straggler_delay(self, prob: float, usec: float, seed: int = 12345,
                                 stream: Optional[torch.cuda.Stream] = None) -> None:

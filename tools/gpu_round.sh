@@ -59,6 +59,10 @@ if has trace; then
   echo "trace exit=$?"; cat gpurun_out/timeline.txt
 fi
 
+if has dgradtl; then
+  timeout 120 python tools/gpu_timeline_dgrad.py > gpurun_out/dgrad_timeline.txt 2>&1; cat gpurun_out/dgrad_timeline.txt
+fi
+
 if has sweep; then
   DM_SWEEP_MAX=${DM_SWEEP_MAX:-67108864} timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$GPUS" \
       --master-addr 127.0.0.1 --master-port 29519 tools/allreduce_sweep.py > gpurun_out/sweep_$GPUS.log 2>&1
