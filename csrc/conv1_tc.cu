@@ -55,11 +55,16 @@ DMNIST_DEVICE void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
                : "memory");
 }
 
-// Build two of the four im2col rows of pooled pixel P (thread = row m of the tile): window positions p = 2h, 2h+1
-// (conv row 2ph + h) into A_{2h}, A_{2h+1}.  Two threads share a pooled pixel, one per h, so a tile has 256 builders.
-DMNIST_DEVICE void build_im2col_half(uint8_t* a_tiles, int m, int h, long long P, long long total,
-                                     const float* __restrict__ images) {
-  float patch[5][6];                                  // input rows 2ph-2+h .. 2ph+2+h, columns 2pw-2 .. 2pw+3
+// The im2col rows of pooled pixel P (thread = row m of the tile) for window positions p = 2h, 2h+1 (conv row 2ph + h)
+// go to A_{2h}, A_{2h+1}.  Two threads share a pooled pixel, one per h, so a tile has 256 builders.  Loading and
+// packing are separate steps: the loop prefetches the next tile's patch (global loads in flight) while it packs and
+// stores the current one, so a builder pays the load latency once per CTA instead of once per tile.
+struct PatchRegs {
+  float v[5][6];        // input rows 2ph-2+h .. 2ph+2+h, columns 2pw-2 .. 2pw+3
+  float one;            // 1.0 for real pixels (tap 25 = bias / ones column), 0 for padding rows of the last tile
+};
+
+DMNIST_DEVICE void load_patch_half(PatchRegs& pr, int h, long long P, long long total, const float* __restrict__ images) {
   if (P < total) {
     const int b = (int)(P / 196), pos = (int)(P - (long long)b * 196);
     const int ph = pos / 14, pw = pos - ph * 14;
@@ -72,25 +77,29 @@ DMNIST_DEVICE void build_im2col_half(uint8_t* a_tiles, int m, int h, long long P
         const int x = 2 * pw - 2 + 2 * c2;           // even: the pair (x, x+1) is inside or outside as a whole
         float2 v = make_float2(0.f, 0.f);
         if (y >= 0 && y < 28 && x >= 0 && x < 28) v = __ldg(reinterpret_cast<const float2*>(img + y * 28 + x));
-        patch[r][2 * c2] = v.x;
-        patch[r][2 * c2 + 1] = v.y;
+        pr.v[r][2 * c2] = v.x;
+        pr.v[r][2 * c2 + 1] = v.y;
       }
     }
+    pr.one = 1.f;
   } else {
 #pragma unroll
     for (int r = 0; r < 5; ++r)
 #pragma unroll
-      for (int c = 0; c < 6; ++c) patch[r][c] = 0.f;
+      for (int c = 0; c < 6; ++c) pr.v[r][c] = 0.f;
+    pr.one = 0.f;
   }
-  const float one = P < total ? 1.f : 0.f;
+}
+
+DMNIST_DEVICE void store_im2col_half(uint8_t* a_tiles, int m, int h, const PatchRegs& pr) {
 #pragma unroll
   for (int px = 0; px < 2; ++px) {
     uint32_t w[16];                                   // 32 taps as bf16 pairs
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int t0 = 2 * j, t1 = 2 * j + 1;
-      const float v0 = t0 < 25 ? patch[t0 / 5][px + t0 % 5] : (t0 == 25 ? one : 0.f);
-      const float v1 = t1 < 25 ? patch[t1 / 5][px + t1 % 5] : (t1 == 25 ? one : 0.f);
+      const float v0 = t0 < 25 ? pr.v[t0 / 5][px + t0 % 5] : (t0 == 25 ? pr.one : 0.f);
+      const float v1 = t1 < 25 ? pr.v[t1 / 5][px + t1 % 5] : (t1 == 25 ? pr.one : 0.f);
       w[j] = pack_bf16x2(v0, v1);
     }
     uint8_t* tile = a_tiles + (2 * h + px) * C1T_AP_BYTES;
@@ -190,13 +199,18 @@ conv1_fwd_tc_kernel(const float* __restrict__ images,   // [B,28,28] fp32
   } else if (warp <= 8) {
     // ------------------------------ operand builders (generic proxy -> fence -> mbarrier) ----------------------
     const int h = (warp - 1) >> 2, m = ((warp - 1) & 3) * 32 + lane;
+    PatchRegs cur, nxt;
+    load_patch_half(cur, h, (long long)blockIdx.x * C1T_TILE + m, total, images);
     int i = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
       const int s = i & 1;
+      const int tn = t + gridDim.x;
+      if (tn < num_tiles) load_patch_half(nxt, h, (long long)tn * C1T_TILE + m, total, images);   // in flight during the stores
       mbar_wait_wd(&a_empty[s], ((i >> 1) & 1) ^ 1);
-      build_im2col_half(smem + C1FwSmem::A_OFF + s * 4 * C1T_AP_BYTES, m, h, (long long)t * C1T_TILE + m, total, images);
+      store_im2col_half(smem + C1FwSmem::A_OFF + s * 4 * C1T_AP_BYTES, m, h, cur);
       fence_proxy_async_smem();
       mbar_arrive(&a_full[s]);
+      cur = nxt;
     }
   } else {
     // ------------------------------ epilogue: max-pool in registers, bias, ReLU, argmax code ----------------------
@@ -312,23 +326,37 @@ conv1_wgrad_tc_kernel(const float* __restrict__ images,          // [B,28,28]
     }
   } else {
     const int h = (warp - 1) >> 2, m = ((warp - 1) & 3) * 32 + lane;   // two builders per pooled pixel: window rows h = 0, 1
-    for (int i = 0; i < nt; ++i) {
-      const int s = i & 1;
-      uint8_t* stage = smem + s * C1WgSmem::STAGE_BYTES;
+    struct TileRegs {
+      PatchRegs patch;
+      uint4 gq[4];      // pooled gradient, 32 channels bf16
+      uint4 cq[2];      // pooling codes, 32 channels
+    };
+    auto load_tile = [&](TileRegs& tr, int i) {
       const long long P = (long long)(t_begin + i) * C1T_TILE + m;
-      // global loads first (independent of the stage being free)
-      uint4 gq[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-      uint4 cq[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+      load_patch_half(tr.patch, h, P, total, images);
       if (P < total) {
         const uint4* gp = reinterpret_cast<const uint4*>(dpool + (size_t)P * 32);
         const uint4* cp = reinterpret_cast<const uint4*>(code + (size_t)P * 32);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) gq[j] = gp[j];
-        cq[0] = __ldg(cp);
-        cq[1] = __ldg(cp + 1);
+        for (int j = 0; j < 4; ++j) tr.gq[j] = gp[j];
+        tr.cq[0] = __ldg(cp);
+        tr.cq[1] = __ldg(cp + 1);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tr.gq[j] = make_uint4(0, 0, 0, 0);
+        tr.cq[0] = tr.cq[1] = make_uint4(0, 0, 0, 0);
       }
+    };
+    TileRegs cur, nxt;
+    if (nt > 0) load_tile(cur, 0);
+    for (int i = 0; i < nt; ++i) {
+      const int s = i & 1;
+      uint8_t* stage = smem + s * C1WgSmem::STAGE_BYTES;
+      if (i + 1 < nt) load_tile(nxt, i + 1);        // next tile's global loads are in flight while this one is packed
       mbar_wait_wd(&empty[s], ((i >> 1) & 1) ^ 1);
-      build_im2col_half(stage, m, h, P, total, images);
+      store_im2col_half(stage, m, h, cur.patch);
+      const uint4* gq = cur.gq;
+      const uint4* cq = cur.cq;
       const uint32_t g32[16] = {gq[0].x, gq[0].y, gq[0].z, gq[0].w, gq[1].x, gq[1].y, gq[1].z, gq[1].w,
                                 gq[2].x, gq[2].y, gq[2].z, gq[2].w, gq[3].x, gq[3].y, gq[3].z, gq[3].w};
       const uint32_t cw[8] = {cq[0].x, cq[0].y, cq[0].z, cq[0].w, cq[1].x, cq[1].y, cq[1].z, cq[1].w};
@@ -349,6 +377,7 @@ conv1_wgrad_tc_kernel(const float* __restrict__ images,          // [B,28,28]
       }
       fence_proxy_async_smem();
       mbar_arrive(&full[s]);
+      cur = nxt;
     }
     if (nt > 0 && warp == 4) {
       // accumulator rows 0-31 = taps (25 = bias); this warp owns TMEM lanes 0-31

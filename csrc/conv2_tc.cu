@@ -30,9 +30,17 @@ constexpr int FW_A_BYTES = 20 * 12 * 32 * 2;   // ONE patch per tile: 20 rows x 
 struct FwSmem {
   static constexpr int A_OFF = W_BYTES;
   static constexpr int BAR_OFF = A_OFF + FW_STAGES * FW_A_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 512 + 1024;
+  static constexpr int SCR_OFF = BAR_OFF + 512;                 // epilogue transpose scratch: 4 warps x 32 rows x 128 B
+  static constexpr int BIAS_OFF = SCR_OFF + 4 * 4096;           // 64 floats
+  static constexpr int TOTAL = BIAS_OFF + 256 + 1024;
 };
 
+// EPI = 1: the 2x2 max-pool is an in-thread max.  Each epilogue warp transposes its 32 pixels x 32 channels through a
+//   swizzled 4 KB shared-memory scratch so that a lane ends up with ALL FOUR window positions of the 8 channels it stores
+//   (8 STS.128 + 8 LDS.128 per chunk) -- ~200 instructions per 32-channel chunk.
+// EPI = 0: first version, 2 warp shuffles + selects per value (~560 instructions per chunk; with one warp per scheduler
+//   the epilogue, not the MMAs, set the kernel's pace: 1.8 us vs 1.25 us per tile).
+template <int EPI>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv2_fwd_kernel(const __grid_constant__ CUtensorMap tmX,   // a1 NHWC [B,14,14,32], box (32,12,20,1), 64B swizzle
                  const __grid_constant__ CUtensorMap tmW,   // W [800][64], box (64,200), 128B swizzle
@@ -48,6 +56,7 @@ conv2_fwd_kernel(const __grid_constant__ CUtensorMap tmX,   // a1 NHWC [B,14,14,
   uint64_t* acc_empty = acc_full + 2;         // [2]
   uint64_t* w_full = acc_empty + 2;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(w_full + 1);
+  float* s_bias = reinterpret_cast<float*>(smem + FwSmem::BIAS_OFF);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -59,6 +68,7 @@ conv2_fwd_kernel(const __grid_constant__ CUtensorMap tmX,   // a1 NHWC [B,14,14,
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<128>(tmem_holder);
+  if (warp == 2) { s_bias[lane] = __ldg(bias + lane); s_bias[32 + lane] = __ldg(bias + 32 + lane); }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -135,6 +145,47 @@ conv2_fwd_kernel(const __grid_constant__ CUtensorMap tmX,   // a1 NHWC [B,14,14,
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + buf * 64 + c * 32, v);
         tmem_ld_wait();
+        if (EPI == 1) {
+          uint8_t* scr = smem + FwSmem::SCR_OFF + q * 4096;
+          __syncwarp();                                   // previous chunk's reads are done
+#pragma unroll
+          for (int k = 0; k < 8; ++k)                     // row = lane (pixel), 16-byte chunk k at k ^ (lane & 7)
+            *reinterpret_cast<uint4*>(scr + lane * 128 + ((k ^ (lane & 7)) << 4)) = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          __syncwarp();
+          const int l0 = lane & ~9;                       // lane of window position 0 (dy = 0, dx = 0)
+          float val[4][8];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const int rp = l0 + (p & 1) + 8 * (p >> 1);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float4 t = *reinterpret_cast<const float4*>(scr + rp * 128 + (((2 * qp + e) ^ (rp & 7)) << 4));
+              val[p][4 * e] = t.x; val[p][4 * e + 1] = t.y; val[p][4 * e + 2] = t.z; val[p][4 * e + 3] = t.w;
+            }
+          }
+          if (valid) {
+            uint32_t pk[4];
+            uint32_t cd[2] = {0u, 0u};
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              float m = val[0][jj];
+              uint32_t idx = 0;
+#pragma unroll
+              for (int p = 1; p < 4; ++p)
+                if (val[p][jj] > m) { m = val[p][jj]; idx = p; }
+              m += s_bias[c * 32 + qp * 8 + jj];
+              const bool active = m > 0.f;
+              cd[jj >> 2] |= (idx | (active ? 4u : 0u)) << ((jj & 3) * 8);
+              const float o = active ? m : 0.f;
+              if (jj & 1) pk[jj >> 1] = pack_bf16x2(__uint_as_float(pk[jj >> 1]), o);
+              else pk[jj >> 1] = __float_as_uint(o);
+            }
+            const size_t off = (((size_t)img * 7 + ph) * 7 + pw) * 64 + c * 32 + qp * 8;
+            *reinterpret_cast<uint4*>(out + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint2*>(code + off) = make_uint2(cd[0], cd[1]);
+          }
+          continue;
+        }
         uint32_t bits0 = 0, bits1 = 0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -337,11 +388,17 @@ struct WgSmem {
   static constexpr int TOTAL = BAR_OFF + 256 + 1024 + 4096;     // + slack: group 6's padding chunks read past the patch
 };
 
+// GPC = tap groups per CTA.  Every group of a CTA reuses the stage's patch + dY tile, so the shared-memory fill traffic
+// (the bound of the first version: 7 groups x 21 pixel slices re-read X and dY seven times = 111 MB through L2 per step at
+// batch 256) drops to ceil(7 / GPC) passes, at the price of ceil(7 / GPC) x fewer pixel slices, i.e. more atomics per output.
+template <int GPC>
 __global__ void __launch_bounds__(CV_THREADS, 1)
 conv2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,    // a1, box (32,12,20,1), 64B swizzle
                    const __grid_constant__ CUtensorMap tmDY,   // dY, box (64,8,16,1), 128B swizzle
                    float* __restrict__ g_w,                    // [25][32][64] fp32, accumulated atomically
                    int num_tiles, int splits) {
+  constexpr int SETS = (WG_GROUPS + GPC - 1) / GPC;
+  constexpr uint32_t TM_COLS = GPC * 64 <= 64 ? 64 : (GPC * 64 <= 128 ? 128 : (GPC * 64 <= 256 ? 256 : 512));
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + WgSmem::BAR_OFF);
@@ -349,13 +406,12 @@ conv2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,    // a1, box (32,12
   uint64_t* acc_full = empty + WG_STAGES;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_full + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int group = blockIdx.x % WG_GROUPS, split = blockIdx.x / WG_GROUPS;
+  const int set = blockIdx.x % SETS, split = blockIdx.x / SETS;
+  const int g_first = set * GPC;
+  const int ng = (g_first + GPC <= WG_GROUPS) ? GPC : (WG_GROUPS - g_first);   // groups this CTA really owns
   const int t_begin = (int)(((long long)num_tiles * split) / splits);
   const int t_end = (int)(((long long)num_tiles * (split + 1)) / splits);
   const int nt = t_end - t_begin;
-  // first tap of the group (as a pixel offset into the patch) and the byte distance between its four M-chunks
-  const int base_px = group < 5 ? group : (group == 5 ? 4 * 12 : 4 * 12 + 4);
-  const uint32_t lbo = group < 5 ? 768u : 64u;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -364,7 +420,7 @@ conv2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,    // a1, box (32,12
     mbar_init(acc_full, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<64>(tmem_holder);
+  if (warp == 1) tmem_alloc<TM_COLS>(tmem_holder);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -391,16 +447,24 @@ conv2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,    // a1, box (32,12
       mbar_wait(&full[s], (i / WG_STAGES) & 1);
       tc_fence_after_sync();
       if (elect_one()) {
-        const uint32_t a_addr = smem_u32(smem + s * WG_STAGE_BYTES) + base_px * 64;
         const uint32_t b_addr = smem_u32(smem + s * WG_STAGE_BYTES) + WG_A_BYTES + 1024;
-        // A (MN-major, 64B swizzle): k = pixel; 8-pixel groups (one tile row) are one patch row = 768 B apart,
-        //   M-chunks (taps) `lbo` apart; a K step = 16 pixels = two tile rows = 1536 B.
         // B (MN-major, 128B swizzle): [pixel][64 co], 8-pixel groups 1024 B apart; K step = 2048 B.
-        const uint64_t da0 = make_smem_desc(a_addr, lbo, 768, SWZ_64B);
         const uint64_t db0 = make_smem_desc(b_addr, 8192, 1024, SWZ_128B);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_bf16(tmem_base, da0 + (uint64_t)((1536 * k) >> 4), db0 + (uint64_t)((2048 * k) >> 4), idesc, (i | k) != 0);
+        for (int gi = 0; gi < GPC; ++gi) {
+          if (gi < ng) {
+            const int group = g_first + gi;
+            // first tap of the group (as a pixel offset into the patch) and the byte distance between its four M-chunks
+            const int base_px = group < 5 ? group : (group == 5 ? 4 * 12 : 4 * 12 + 4);
+            const uint32_t lbo = group < 5 ? 768u : 64u;
+            // A (MN-major, 64B swizzle): k = pixel; 8-pixel groups (one tile row) are one patch row = 768 B apart,
+            //   M-chunks (taps) `lbo` apart; a K step = 16 pixels = two tile rows = 1536 B.
+            const uint64_t da0 = make_smem_desc(smem_u32(smem + s * WG_STAGE_BYTES) + base_px * 64, lbo, 768, SWZ_64B);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_bf16(tmem_base + gi * 64, da0 + (uint64_t)((1536 * k) >> 4), db0 + (uint64_t)((2048 * k) >> 4), idesc, (i | k) != 0);
+          }
+        }
         umma_commit(&empty[s]);
         if (i == nt - 1) umma_commit(acc_full);
       }
@@ -410,24 +474,28 @@ conv2_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,    // a1, box (32,12
     const int q = warp & 3;               // rows 32q .. 32q+31 = M-chunk q of the group, row = ci
     mbar_wait(acc_full, 0);
     tc_fence_after_sync();
-    const int tap = group < 5 ? q * 5 + group : (group == 5 ? 20 + q : (q == 0 ? 24 : 25));
 #pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, v);
-      tmem_ld_wait();
-      if (tap < 25) {
-        float* o = g_w + ((size_t)tap * 32 + lane) * 64 + c * 32;
+    for (int gi = 0; gi < ng; ++gi) {
+      const int group = g_first + gi;
+      const int tap = group < 5 ? q * 5 + group : (group == 5 ? 20 + q : (q == 0 ? 24 : 25));
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + gi * 64 + c * 32, v);
+        tmem_ld_wait();
+        if (tap < 25) {
+          float* o = g_w + ((size_t)tap * 32 + lane) * 64 + c * 32;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          red_add_f32x4(o + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                        __uint_as_float(v[j + 3]));
+          for (int j = 0; j < 32; j += 4)
+            red_add_f32x4(o + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                          __uint_as_float(v[j + 3]));
+        }
       }
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<64>(tmem_base);
+  if (warp == 1) tmem_dealloc<TM_COLS>(tmem_base);
 }
 
 }  // namespace dm
@@ -440,14 +508,17 @@ int dm_conv2_fwd(const void* a1, const void* w_bf16, const void* bias, void* out
   CUtensorMap tmX, tmW;
   if (make_tmap_nhwc_bf16(&tmX, a1, 32, 14, 14, B, 32, 12, 20, 64)) return 101;
   if (make_tmap_2d_bf16(&tmW, w_bf16, 64, 800, 64, 64, 200, 128)) return 102;
+  static const int epi = env_int("DMNIST_CONV2_EPI", 1);
   static bool configured = false;
   if (!configured) {
-    DM_CUDA_OK(cudaFuncSetAttribute(conv2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwSmem::TOTAL));
+    DM_CUDA_OK(cudaFuncSetAttribute(conv2_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwSmem::TOTAL));
+    DM_CUDA_OK(cudaFuncSetAttribute(conv2_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwSmem::TOTAL));
     configured = true;
   }
   const int tiles = 2 * B;
   const int grid = tiles < 148 ? tiles : 148;
-  return (int)launch_kernel(conv2_fwd_kernel, dim3(grid), dim3(CV_THREADS), FwSmem::TOTAL,
+  auto kern = epi == 0 ? conv2_fwd_kernel<0> : conv2_fwd_kernel<1>;
+  return (int)launch_kernel(kern, dim3(grid), dim3(CV_THREADS), FwSmem::TOTAL,
                             reinterpret_cast<cudaStream_t>(stream), tmX, tmW, reinterpret_cast<const float*>(bias),
                             reinterpret_cast<__nv_bfloat16*>(out), reinterpret_cast<uint8_t*>(code), tiles);
 }
@@ -480,16 +551,23 @@ int dm_conv2_wgrad(const void* a1, const void* dy, void* g_w, int B, void* strea
   CUtensorMap tmX, tmDY;
   if (make_tmap_nhwc_bf16(&tmX, a1, 32, 14, 14, B, 32, 12, 20, 64)) return 101;
   if (make_tmap_nhwc_bf16(&tmDY, dy, 64, 14, 14, B, 64, 8, 16, 128)) return 102;
+  const int tiles = 2 * B;
+  static const int gpc = env_int("DMNIST_WGRAD_GPC", 2);      // tap groups per CTA: 1 (first version), 2, 4
+  const int sets = gpc == 1 ? 7 : (gpc == 2 ? 4 : 2);
+  int splits = g_max_ctas / sets;
+  if (splits > tiles) splits = tiles;
   static bool configured = false;
   if (!configured) {
-    DM_CUDA_OK(cudaFuncSetAttribute(conv2_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem::TOTAL));
+    DM_CUDA_OK(cudaFuncSetAttribute(conv2_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem::TOTAL));
+    DM_CUDA_OK(cudaFuncSetAttribute(conv2_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem::TOTAL));
+    DM_CUDA_OK(cudaFuncSetAttribute(conv2_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem::TOTAL));
     configured = true;
   }
-  const int tiles = 2 * B;
-  int splits = g_max_ctas / WG_GROUPS;   // 148 SMs: 21 -> 147 CTAs
-  if (splits > tiles) splits = tiles;
-  return (int)launch_kernel(conv2_wgrad_kernel, dim3(WG_GROUPS * splits), dim3(CV_THREADS), WgSmem::TOTAL,
-                            reinterpret_cast<cudaStream_t>(stream), tmX, tmDY, reinterpret_cast<float*>(g_w), tiles, splits);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float* gw = reinterpret_cast<float*>(g_w);
+  if (gpc == 1) return (int)launch_kernel(conv2_wgrad_kernel<1>, dim3(sets * splits), dim3(CV_THREADS), WgSmem::TOTAL, st, tmX, tmDY, gw, tiles, splits);
+  if (gpc == 2) return (int)launch_kernel(conv2_wgrad_kernel<2>, dim3(sets * splits), dim3(CV_THREADS), WgSmem::TOTAL, st, tmX, tmDY, gw, tiles, splits);
+  return (int)launch_kernel(conv2_wgrad_kernel<4>, dim3(sets * splits), dim3(CV_THREADS), WgSmem::TOTAL, st, tmX, tmDY, gw, tiles, splits);
 }
 
 }  // extern "C"

@@ -429,10 +429,13 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_sgd_kernel(SyncPee
 // The exposed communication per step is one flag hop + one round trip on 208 KB instead of the whole 6.6 MB exchange.
 // =====================================================================================================================
 struct BucketArgs {
-  int begin4, end4;           // this kernel's range of the arena, in float4
-  int early_begin4, early_end4;   // (late kernel) the early bucket, for the shadow refresh
+  int begin4, end4;               // early kernel: the early bucket; late kernel: the whole arena (float4 units)
+  int early_begin4, early_end4;   // late kernel: the early bucket (skipped by the one-shot, refreshed in the shadow)
 };
 
+// NR = number of replicas (compile time so the peer loop keeps 16 independent 16-byte loads in flight per thread:
+// 20 CTAs must cover the NVLink bandwidth-delay product on their own)
+template <int NR>
 __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_early_kernel(SyncPeers P, SyncArgs a, BucketArgs r) {
   SyncCtrl* me = P.ctrl[a.rank];
   __shared__ uint32_t s_last;
@@ -456,7 +459,7 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_early_kernel(SyncP
   const float* wsrc = P.params[a.rank];
   const int stride = gridDim.x * SYNC_THREADS;
   if (a.mc_grads != nullptr && a.mc_params != nullptr) {
-    constexpr int V = 4;
+    constexpr int V = 8;
     for (int i0 = begin + blockIdx.x * SYNC_THREADS + threadIdx.x; i0 < end; i0 += V * stride) {
       float4 g[V], w[V];
 #pragma unroll
@@ -483,15 +486,15 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_early_kernel(SyncP
       }
     }
   } else {
-    constexpr int U = 2;
+    constexpr int U = 16 / NR;
     for (int i0 = begin + blockIdx.x * SYNC_THREADS + threadIdx.x; i0 < end; i0 += U * stride) {
-      float4 g[U][SYNC_MAX_RANKS], w[U];
+      float4 g[U][NR], w[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int i = i0 + u * stride;
 #pragma unroll
-        for (int c = 0; c < SYNC_MAX_RANKS; ++c)
-          g[u][c] = (c < a.nranks && i < end) ? ld_peer_f4(P.grads[c] + 4 * (size_t)i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < NR; ++c)
+          g[u][c] = i < end ? ld_peer_f4(P.grads[c] + 4 * (size_t)i) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < end) w[u] = *reinterpret_cast<const float4*>(wsrc + 4 * (size_t)i);
       }
 #pragma unroll
@@ -500,11 +503,11 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_early_kernel(SyncP
         if (i >= end) continue;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < SYNC_MAX_RANKS; ++c)
-          if (c < a.nranks) { acc.x += g[u][c].x; acc.y += g[u][c].y; acc.z += g[u][c].z; acc.w += g[u][c].w; }
+        for (int c = 0; c < NR; ++c) { acc.x += g[u][c].x; acc.y += g[u][c].y; acc.z += g[u][c].z; acc.w += g[u][c].w; }
         float4 nw = w[u];
         nw.x -= scale * acc.x; nw.y -= scale * acc.y; nw.z -= scale * acc.z; nw.w -= scale * acc.w;
-        for (int q = 0; q < a.nranks; ++q) st_peer_f4(P.params[q] + 4 * (size_t)i, nw);
+#pragma unroll
+        for (int q = 0; q < NR; ++q) st_peer_f4(P.params[q] + 4 * (size_t)i, nw);
         if (a.shadow != nullptr) {
           uint2 o;
           o.x = pack_bf16x2(nw.x, nw.y);
@@ -550,7 +553,11 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_late_kernel(SyncPe
   const float scale = device_lr(a, epoch) / (float)a.nranks;
   float* wdst = P.params[a.rank];
   const int stride = gridDim.x * SYNC_THREADS;
-  for (int i = r.begin4 + blockIdx.x * SYNC_THREADS + threadIdx.x; i < r.end4; i += stride) {
+  // late bucket = [begin4, end4) minus the early range: walk a compacted index
+  const int early_n = r.early_end4 - r.early_begin4;
+  const int n_late = (r.end4 - r.begin4) - early_n;
+  for (int j = blockIdx.x * SYNC_THREADS + threadIdx.x; j < n_late; j += stride) {
+    const int i = (r.begin4 + j < r.early_begin4) ? r.begin4 + j : r.begin4 + j + early_n;
     float4 g[SYNC_MAX_RANKS];
 #pragma unroll
     for (int c = 0; c < SYNC_MAX_RANKS; ++c)
@@ -715,7 +722,12 @@ int dm_fused_sync_bucket(void* const* ctrl, void* const* params, void* const* gr
   r.early_begin4 = (int)(early_begin / 4); r.early_end4 = (int)(early_end / 4);
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (ctas < 1) ctas = phase == 1 ? 20 : 148;
-  if (phase == 1) return (int)launch_kernel(fused_sync_early_kernel, dim3(ctas), dim3(SYNC_THREADS), 0, stream, P, a, r);
+  if (phase == 1) {
+    if (nranks == 2) return (int)launch_kernel(fused_sync_early_kernel<2>, dim3(ctas), dim3(SYNC_THREADS), 0, stream, P, a, r);
+    if (nranks == 4) return (int)launch_kernel(fused_sync_early_kernel<4>, dim3(ctas), dim3(SYNC_THREADS), 0, stream, P, a, r);
+    if (nranks == 8) return (int)launch_kernel(fused_sync_early_kernel<8>, dim3(ctas), dim3(SYNC_THREADS), 0, stream, P, a, r);
+    return -5;     // bucketed path is instantiated for 2, 4 and 8 replicas; the caller falls back to the single kernel
+  }
   return (int)launch_kernel(fused_sync_late_kernel, dim3(ctas), dim3(SYNC_THREADS), 0, stream, P, a, r);
 }
 

@@ -87,7 +87,7 @@ class CudaLeNetEngine(ComputeEngine):
         # the data-gradient chain is the critical path: it is captured on a high-priority stream, the weight-gradient
         # side branches on low-priority ones, so the block scheduler serves the chain first whenever both have CTAs pending
         lo, hi = (0, -1)
-        self._side = [torch.cuda.Stream(device=dev, priority=lo) for _ in range(2)]
+        self._side = [torch.cuda.Stream(device=dev, priority=lo) for _ in range(3)]
         self._main_priority = hi if os.environ.get("DMNIST_PRIO", "1") != "0" else lo
         self._wgrad_late = os.environ.get("DMNIST_WGRAD_LATE", "1") != "0"
         self._branches = os.environ.get("DMNIST_BRANCHES", "1") != "0"
@@ -102,7 +102,9 @@ class CudaLeNetEngine(ComputeEngine):
         p_fc1 = self.spec.param("fc1_weights")
         self._zero_ranges = [(0, p_fc1.offset), (p_fc1.offset + p_fc1.numel, self.spec.arena_numel)]
         self._seed_mix0 = dropout_seed_mix(seed, 0, rank)
-        self._bucket_split = p_fc1.offset          # [0, split) = conv parameters (late bucket), [split, end) = fc (early)
+        # early bucket = fc1_weights (96.5 % of the bytes, final as soon as fc1_wgrad is done); everything else is late
+        self._bucket_split = p_fc1.offset
+        self._bucket_early = (p_fc1.offset, p_fc1.offset + p_fc1.numel)
         self._bucketed = False
         self._epoch_ptr = ctypes.c_void_p(backend.ctrl.local_ptr + backend._off["epoch"])
         self.launches_per_step = 0
@@ -150,7 +152,7 @@ class CudaLeNetEngine(ComputeEngine):
         # Bucketed aggregation (csrc/fused_sync.cu): full participation on more than one replica.  The fc bucket (96.9 % of
         # the bytes) is exchanged by a 20-CTA kernel NEXT TO conv2 dgrad/wgrad + conv1 wgrad, which are capped at 128 CTAs.
         n = self.backend.ctx.world_size
-        self._bucketed = (hasattr(self, "_bucket_split") and n > 1 and int(k) == n and self._branches
+        self._bucketed = (hasattr(self, "_bucket_split") and n in (2, 4, 8) and int(k) == n and self._branches
                           and self.backend.drop_keep <= 0.0 and os.environ.get("DMNIST_BUCKET", "1") != "0")
         self._early_ctas = int(os.environ.get("DMNIST_EARLY_CTAS", "20"))
         self.lib.dm_set_max_ctas(148 - self._early_ctas if self._bucketed else 148)
@@ -195,9 +197,10 @@ class CudaLeNetEngine(ComputeEngine):
             # fc1 wgrad: dW1[3136,512] = a2^T (A MN-major) * dh (B MN-major), K = batch; straight into the arena
             G.gemm_bf16_raw(self.a2, self.dh, g["fc1_weights"], 3136, 512, B, 3136, 512, 512, True, True,
                             G.EPI_STORE_F32, bn=128)
-            # fc2 weight/bias + fc1 bias gradients: only the aggregation kernel consumes them
-            check(lib.dm_fc2_wgrad(ptr(self.h_act), ptr(self.dlogits), ptr(self.dh), ptr(g["fc2_weights"]),
-                                   ptr(g["fc2_biases"]), ptr(g["fc1_biases"]), B, stream_ptr()), "fc2_wgrad")
+            if not early_sync:
+                # fc2 weight/bias + fc1 bias gradients: only the aggregation kernel consumes them
+                check(lib.dm_fc2_wgrad(ptr(self.h_act), ptr(self.dlogits), ptr(self.dh), ptr(g["fc2_weights"]),
+                                       ptr(g["fc2_biases"]), ptr(g["fc1_biases"]), B, stream_ptr()), "fc2_wgrad")
             if branch and not early_sync:
                 join1 = torch.cuda.Event()
                 join1.record(self._side[0])
@@ -221,11 +224,18 @@ class CudaLeNetEngine(ComputeEngine):
                 if self._straggler is not None:
                     self.backend.enqueue_straggler_delay(self._straggler.prob, self._straggler.usec, stream=self._side[0])
                 oa = self._opt_args
-                self.backend.enqueue_bucket(self.params, self.grads, 1, self._bucket_split, self.spec.arena_numel,
-                                            self._bucket_split, self.spec.arena_numel, oa["lr0"], oa["decay_rate"],
+                e0, e1 = self._bucket_early
+                self.backend.enqueue_bucket(self.params, self.grads, 1, e0, e1, e0, e1, oa["lr0"], oa["decay_rate"],
                                             oa["decay_steps"], ctas=self._early_ctas, stream=self._side[0])
                 join1 = torch.cuda.Event()
                 join1.record(self._side[0])
+            # the small fc gradients (fc2 weights/biases, fc1 biases) belong to the late bucket: their own branch
+            self._side[2].wait_event(fork1)
+            with torch.cuda.stream(self._side[2]):
+                check(lib.dm_fc2_wgrad(ptr(self.h_act), ptr(self.dlogits), ptr(self.dh), ptr(g["fc2_weights"]),
+                                       ptr(g["fc2_biases"]), ptr(g["fc1_biases"]), B, stream_ptr()), "fc2_wgrad")
+                join3 = torch.cuda.Event()
+                join3.record(self._side[2])
         late = branch and self._wgrad_late
         if late:
             # conv2 dgrad and wgrad each fill the machine (1 CTA/SM, ~200 KB smem): side by side they only slow the chain
@@ -248,6 +258,8 @@ class CudaLeNetEngine(ComputeEngine):
         if branch:
             main.wait_event(join1)
             main.wait_event(join2)
+            if early_sync:
+                main.wait_event(join3)
         return 6 if self._fuse_unpool else 7
 
     def _zero_args(self, train: bool):
@@ -342,8 +354,9 @@ class CudaLeNetEngine(ComputeEngine):
         n += self._launch_backward(self.images[slot], self.batch_size, early_sync=bucketed)
         if bucketed:
             oa = self._opt_args
-            self.backend.enqueue_bucket(self.params, self.grads, 2, 0, self._bucket_split, self._bucket_split,
-                                        self.spec.arena_numel, oa["lr0"], oa["decay_rate"], oa["decay_steps"])
+            e0, e1 = self._bucket_early
+            self.backend.enqueue_bucket(self.params, self.grads, 2, 0, self.spec.arena_numel, e0, e1,
+                                        oa["lr0"], oa["decay_rate"], oa["decay_steps"])
             n += 2 + (1 if self._straggler is not None else 0)
         elif with_sync:
             if self._straggler is not None:

@@ -43,7 +43,7 @@ def main():
         torch.cuda.synchronize()
         rows.append({"step": info.global_step, "mask": info.mask, "count": info.count, "loss": loss,
                      "fp": fp(eng.params), "shadow_err": (eng.shadow.float() - eng.params).abs().max().item(),
-                     "pmax": eng.params.abs().max().item()})
+                     "pmax": eng.params.abs().max().item(), "sample": eng.params[::40009].cpu().tolist()})
     be.check_error()
     json.dump({"rank": r, "bucketed": bool(eng._bucketed), "nvls": bool(be.nvls_active), "rows": rows,
                "params_sum": eng.params.double().sum().item(), "sample": eng.params[::40009].cpu().tolist()},

@@ -131,7 +131,12 @@ def test_bucketed_overlapped_aggregation_matches_single_kernel(tmp_path):
             assert len({x["fp"] for x in rows}) == 1, (tag, s)                   # replicas bit-identical
             assert all(x["step"] == s + 1 and x["count"] == n and x["mask"] == (1 << n) - 1 for x in rows), (tag, rows)
             assert all(x["shadow_err"] <= 0.01 * x["pmax"] + 1e-6 for x in rows), (tag, rows)
-    a, b, c = (torch.tensor(res[t][0]["sample"]) for t in ("bucket_nvls", "bucket", "single"))
-    assert (b - c).abs().max().item() < 1e-6          # same sums in the same order
-    assert (a - b).abs().max().item() < 1e-4
+    # across RUNS the gradients differ in the last bits (fp32 atomics in the conv weight gradients, different CTA counts),
+    # so paths are compared tightly after the first update and loosely after eight
+    first = {t: torch.tensor(res[t][0]["rows"][0]["sample"]) for t in res}
+    last = {t: torch.tensor(res[t][0]["rows"][-1]["sample"]) for t in res}
+    assert (first["bucket"] - first["single"]).abs().max().item() < 2e-6
+    assert (first["bucket_nvls"] - first["bucket"]).abs().max().item() < 2e-6
+    assert (last["bucket"] - last["single"]).abs().max().item() < 2e-2
+    assert (last["bucket_nvls"] - last["bucket"]).abs().max().item() < 2e-2
     assert res["bucket"][0]["rows"][-1]["loss"] == res["bucket"][0]["rows"][-1]["loss"]      # not NaN
