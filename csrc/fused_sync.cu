@@ -433,10 +433,16 @@ struct BucketArgs {
   int early_begin4, early_end4;   // late kernel: the early bucket (skipped by the one-shot, refreshed in the shadow)
 };
 
-// NR = number of replicas (compile time so the peer loop keeps 16 independent 16-byte loads in flight per thread:
-// 20 CTAs must cover the NVLink bandwidth-delay product on their own)
+// NR = number of replicas (compile time: the peer loop keeps 16 independent 16-byte loads in flight per thread).
+// CTAs are SMALL (128 threads, <= 128 registers: 16 K registers, no shared memory) and there is one per SM: they fit
+// next to the tensor-core CTAs of conv2 dgrad/wgrad and conv1 wgrad, whose six warps leave the schedulers mostly idle,
+// so the exchange borrows issue slots instead of whole SMs.  (A first version used 20 full-size CTAs on reserved SMs:
+// an SM sustains only ~10 GB/s of peer traffic -- its outstanding-request budget over a ~3 us round trip -- so 20 of
+// them needed 33 us for the 2 x 3.2 MB, longer than the backward pass they were hiding under; see
+// profiles/bench_r1_call26_2gpu_bucketed.txt.)
+constexpr int EARLY_THREADS = 128;
 template <int NR>
-__global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_early_kernel(SyncPeers P, SyncArgs a, BucketArgs r) {
+__global__ void __launch_bounds__(EARLY_THREADS) fused_sync_early_kernel(SyncPeers P, SyncArgs a, BucketArgs r) {
   SyncCtrl* me = P.ctrl[a.rank];
   __shared__ uint32_t s_last;
   pdl_wait();
@@ -457,10 +463,10 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_early_kernel(SyncP
   const int end = min(begin + shard, r.end4);
   const float scale = device_lr(a, epoch) / (float)a.nranks;
   const float* wsrc = P.params[a.rank];
-  const int stride = gridDim.x * SYNC_THREADS;
+  const int stride = gridDim.x * EARLY_THREADS;
   if (a.mc_grads != nullptr && a.mc_params != nullptr) {
     constexpr int V = 8;
-    for (int i0 = begin + blockIdx.x * SYNC_THREADS + threadIdx.x; i0 < end; i0 += V * stride) {
+    for (int i0 = begin + blockIdx.x * EARLY_THREADS + threadIdx.x; i0 < end; i0 += V * stride) {
       float4 g[V], w[V];
 #pragma unroll
       for (int u = 0; u < V; ++u) {
@@ -487,7 +493,7 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_early_kernel(SyncP
     }
   } else {
     constexpr int U = 16 / NR;
-    for (int i0 = begin + blockIdx.x * SYNC_THREADS + threadIdx.x; i0 < end; i0 += U * stride) {
+    for (int i0 = begin + blockIdx.x * EARLY_THREADS + threadIdx.x; i0 < end; i0 += U * stride) {
       float4 g[U][NR], w[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -721,11 +727,11 @@ int dm_fused_sync_bucket(void* const* ctrl, void* const* params, void* const* gr
   r.begin4 = (int)(begin / 4); r.end4 = (int)(end / 4);
   r.early_begin4 = (int)(early_begin / 4); r.early_end4 = (int)(early_end / 4);
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (ctas < 1) ctas = phase == 1 ? 20 : 148;
+  if (ctas < 1) ctas = 148;
   if (phase == 1) {
-    if (nranks == 2) return (int)launch_kernel(fused_sync_early_kernel<2>, dim3(ctas), dim3(SYNC_THREADS), 0, stream, P, a, r);
-    if (nranks == 4) return (int)launch_kernel(fused_sync_early_kernel<4>, dim3(ctas), dim3(SYNC_THREADS), 0, stream, P, a, r);
-    if (nranks == 8) return (int)launch_kernel(fused_sync_early_kernel<8>, dim3(ctas), dim3(SYNC_THREADS), 0, stream, P, a, r);
+    if (nranks == 2) return (int)launch_kernel(fused_sync_early_kernel<2>, dim3(ctas), dim3(EARLY_THREADS), 0, stream, P, a, r);
+    if (nranks == 4) return (int)launch_kernel(fused_sync_early_kernel<4>, dim3(ctas), dim3(EARLY_THREADS), 0, stream, P, a, r);
+    if (nranks == 8) return (int)launch_kernel(fused_sync_early_kernel<8>, dim3(ctas), dim3(EARLY_THREADS), 0, stream, P, a, r);
     return -5;     // bucketed path is instantiated for 2, 4 and 8 replicas; the caller falls back to the single kernel
   }
   return (int)launch_kernel(fused_sync_late_kernel, dim3(ctas), dim3(SYNC_THREADS), 0, stream, P, a, r);

@@ -149,13 +149,12 @@ class CudaLeNetEngine(ComputeEngine):
         self._straggler = getattr(opt, "_straggler", None)
         self._stamp = getattr(opt, "mode", "") == "cdf"
         self._graphs = [None, None]
-        # Bucketed aggregation (csrc/fused_sync.cu): full participation on more than one replica.  The fc bucket (96.9 % of
-        # the bytes) is exchanged by a 20-CTA kernel NEXT TO conv2 dgrad/wgrad + conv1 wgrad, which are capped at 128 CTAs.
-        n = self.backend.ctx.world_size
+        # Bucketed aggregation (csrc/fused_sync.cu): full participation on 2/4/8 replicas.  fc1's weight gradient (96.5 % of
+        # the bytes) is exchanged by small co-resident CTAs NEXT TO conv2 dgrad/wgrad + conv1 wgrad; the rest goes one-shot.
         self._bucketed = (hasattr(self, "_bucket_split") and n in (2, 4, 8) and int(k) == n and self._branches
                           and self.backend.drop_keep <= 0.0 and os.environ.get("DMNIST_BUCKET", "1") != "0")
-        self._early_ctas = int(os.environ.get("DMNIST_EARLY_CTAS", "20"))
-        self.lib.dm_set_max_ctas(148 - self._early_ctas if self._bucketed else 148)
+        self._early_ctas = int(os.environ.get("DMNIST_EARLY_CTAS", "148"))
+        self.lib.dm_set_max_ctas(int(os.environ.get("DMNIST_MAX_CTAS", "148")))
 
     def params_updated(self) -> None:
         """Parameters were written from the host (init / restore): refresh the bf16 shadow."""

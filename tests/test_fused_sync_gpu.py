@@ -75,10 +75,13 @@ def test_k_of_n_training_through_the_reference_entrypoint(tmp_path):
     assert codes == [0, 0], "\n".join(v[-1500:] for v in logs.values())
     s0 = [int(x) for x in re.findall(r"Worker 0: .*: step ([0-9]+),", logs["out_master"])]
     s1 = [int(x) for x in re.findall(r"Worker 1: .*: step ([0-9]+),", logs["out_worker_0"])]
-    assert s0 and s1 and max(s0) >= 40
-    # the delayed replica logs only the global steps it wakes up in: far fewer local iterations than global steps, each
-    # one fast-forwarded to the newest committed step (reference: stale push dropped, worker proceeds, ...modified.py:87-90)
-    assert s1 == sorted(s1) and len(s1) < len(s0) and max(s1) > len(s1), (s0, s1)
+    # Each replica logs the global steps it took part in or woke up in.  With K = 1 whoever arrives first commits the
+    # step and the other one's gradient is dropped: its next iteration fast-forwards to the newest committed step
+    # (reference: stale push dropped, worker proceeds, ...modified.py:59-62,87-90), so at least one replica logs fewer
+    # local iterations than global steps, and nobody ever goes backwards.
+    assert s0 and s1 and max(max(s0), max(s1)) >= 40, (s0, s1)
+    assert s0 == sorted(set(s0)) and s1 == sorted(set(s1)), (s0, s1)
+    assert len(s0) < max(s0) or len(s1) < max(s1), (s0, s1)
     assert os.path.exists(tmp_path / "train_dir" / "checkpoint")
 
 
