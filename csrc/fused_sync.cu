@@ -729,6 +729,17 @@ int dm_fused_sync_bucket(void* const* ctrl, void* const* params, void* const* gr
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (ctas < 1) ctas = 148;
   if (phase == 1) {
+    // The early kernel must be CO-RESIDENT with the tensor-core kernels of the backward pass, which run with the SM's
+    // L1/shared split at maximum shared memory.  A kernel that (by default) prefers the maximum-L1 split cannot share an
+    // SM with them and would only get SMs as their CTAs exit (observed: profiles/bench_r1_call27_2gpu.txt), so it asks
+    // for the same split although it uses no shared memory.
+    static bool configured = false;
+    if (!configured) {
+      DM_CUDA_OK(cudaFuncSetAttribute(fused_sync_early_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      DM_CUDA_OK(cudaFuncSetAttribute(fused_sync_early_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      DM_CUDA_OK(cudaFuncSetAttribute(fused_sync_early_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      configured = true;
+    }
     if (nranks == 2) return (int)launch_kernel(fused_sync_early_kernel<2>, dim3(ctas), dim3(EARLY_THREADS), 0, stream, P, a, r);
     if (nranks == 4) return (int)launch_kernel(fused_sync_early_kernel<4>, dim3(ctas), dim3(EARLY_THREADS), 0, stream, P, a, r);
     if (nranks == 8) return (int)launch_kernel(fused_sync_early_kernel<8>, dim3(ctas), dim3(EARLY_THREADS), 0, stream, P, a, r);

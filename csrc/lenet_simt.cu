@@ -609,6 +609,12 @@ int dm_fc2_fwd_bwd(const void* h_part, long long part_stride, int splits, const 
 // Side-branch half: g_w2 [512][10], g_b2 [10], g_b1 [512] (plain stores).
 int dm_fc2_wgrad(const void* scratch_h, const void* scratch_dl, const void* dh, void* g_w2, void* g_b2, void* g_b1, int B,
                  void* stream) {
+  // side-branch kernel: it has to share SMs with the tensor-core kernels (max-shared L1 split), see dm_fused_sync_bucket
+  static bool configured = false;
+  if (!configured) {
+    DM_CUDA_OK(cudaFuncSetAttribute(dm::fc2_wgrad_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    configured = true;
+  }
   return (int)dm::launch_kernel(dm::fc2_wgrad_kernel, dim3(dm::HID / dm::FW_J), dim3(256), 0,
                                 reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const float*>(scratch_h),
                                 reinterpret_cast<const float*>(scratch_dl), reinterpret_cast<const __nv_bfloat16*>(dh),

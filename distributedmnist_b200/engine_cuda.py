@@ -60,8 +60,11 @@ class CudaLeNetEngine(ComputeEngine):
         self.pb = self.spec.views(self.shadow)
         bf, u8, f32 = torch.bfloat16, torch.uint8, torch.float32
         # two input slots so the H2D copy of step i+1 overlaps the compute of step i
-        self.images = [torch.zeros(B, 28, 28, dtype=f32, device=dev) for _ in range(2)]
-        self.labels = [torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(2)]
+        # (images and labels of a slot share one allocation so a packed host batch moves with ONE host->device copy)
+        self._in_bytes = B * 784 * 4 + B * 8
+        self.in_dev = [torch.zeros(self._in_bytes, dtype=u8, device=dev) for _ in range(2)]
+        self.images = [t[:B * 784 * 4].view(f32).view(B, 28, 28) for t in self.in_dev]
+        self.labels = [t[B * 784 * 4:].view(torch.int64) for t in self.in_dev]
         self.h_images = [torch.zeros(B, 28, 28, dtype=f32).pin_memory() for _ in range(2)]
         self.h_labels = [torch.zeros(B, dtype=torch.int64).pin_memory() for _ in range(2)]
         self.a1 = torch.zeros(B, 14, 14, 32, dtype=bf, device=dev)
@@ -134,6 +137,30 @@ class CudaLeNetEngine(ComputeEngine):
         self._slot = s
         self._loaded += 1
 
+    def pack_batch(self, images, labels, pin: bool = True) -> torch.Tensor:
+        """One contiguous (page-locked) host buffer holding a batch in the device slot's layout: fp32 images
+        ``[B,28,28]`` followed by int64 labels ``[B]``.  Input pipelines that fill such buffers hand each batch to
+        :meth:`load_packed`, which is a single DMA."""
+        B = self.batch_size
+        buf = torch.empty(self._in_bytes, dtype=torch.uint8)
+        if pin:
+            buf = buf.pin_memory()
+        img = torch.as_tensor(images, dtype=torch.float32).reshape(B * 784)
+        buf[:B * 784 * 4].view(torch.float32).copy_(img)
+        buf[B * 784 * 4:].view(torch.int64).copy_(torch.as_tensor(labels, dtype=torch.int64).reshape(B))
+        return buf
+
+    def load_packed(self, packed: torch.Tensor) -> None:
+        """Packed batch (see :meth:`pack_batch`; pinned host or device memory) -> device slot with one copy on the copy
+        stream.  The buffer must stay untouched until the step after the next one has been enqueued."""
+        s = self._loaded & 1
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self._slot_free[s])
+            self.in_dev[s].copy_(packed, non_blocking=True)
+            self._copy_done[s].record(self.copy_stream)
+        self._slot = s
+        self._loaded += 1
+
     def h2d_bytes_per_step(self) -> int:
         return self._h2d_bytes
 
@@ -151,6 +178,7 @@ class CudaLeNetEngine(ComputeEngine):
         self._graphs = [None, None]
         # Bucketed aggregation (csrc/fused_sync.cu): full participation on 2/4/8 replicas.  fc1's weight gradient (96.5 % of
         # the bytes) is exchanged by small co-resident CTAs NEXT TO conv2 dgrad/wgrad + conv1 wgrad; the rest goes one-shot.
+        n = self.backend.ctx.world_size
         self._bucketed = (hasattr(self, "_bucket_split") and n in (2, 4, 8) and int(k) == n and self._branches
                           and self.backend.drop_keep <= 0.0 and os.environ.get("DMNIST_BUCKET", "1") != "0")
         self._early_ctas = int(os.environ.get("DMNIST_EARLY_CTAS", "148"))
@@ -363,6 +391,9 @@ class CudaLeNetEngine(ComputeEngine):
                 n += 1
             self.backend.enqueue(self.params, self.grads, **self._opt_args)
             n += 1
+        # (loss, accuracy) of the step -> page-locked host buffer of this slot, as part of the step (a memcpy node of the
+        # graph): reading the result costs the host no extra call, only a wait on the step's completion event
+        self.h_loss_bufs[slot].copy_(self.d_loss_acc, non_blocking=True)
         self.launches_per_step = n
 
     def _run(self, with_sync: bool) -> None:
@@ -396,15 +427,11 @@ class CudaLeNetEngine(ComputeEngine):
         self._run(with_sync=True)
 
     def read_loss_async(self):
-        """Queue the device->host copy of (loss, accuracy) into a pinned buffer (two alternate).
-        Returns ``(event, buffer)``: wait on the event, then read ``buffer[0]`` / ``buffer[1]``."""
-        buf = self.h_loss_bufs[self._loss_reads & 1]
-        self._loss_reads += 1
-        buf.copy_(self.d_loss_acc, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        self.h_loss_acc = buf
-        return ev, buf
+        """``(event, buffer)`` of the step enqueued last: the step copies (loss, accuracy) into a pinned host buffer
+        (two alternate, one per input slot) as its final node; wait on the event, then read ``buffer[0]`` / ``buffer[1]``."""
+        s = self._slot                      # the step just enqueued copied its result into this slot's buffer itself
+        self.h_loss_acc = self.h_loss_bufs[s]
+        return self._slot_free[s], self.h_loss_bufs[s]
 
     def loss_acc(self) -> Tuple[float, float]:
         ev, buf = self.read_loss_async()
@@ -461,8 +488,10 @@ class CudaMlpEngine(ComputeEngine):
         self.grads = backend.allocate(self.spec.arena_numel)
         self.shadow = backend.attach_shadow(self.params)
         self.p, self.g, self.pb = (self.spec.views(t) for t in (self.params, self.grads, self.shadow))
-        self.images = [torch.zeros(B, 784, dtype=torch.float32, device=dev) for _ in range(2)]
-        self.labels = [torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(2)]
+        self._in_bytes = B * 784 * 4 + B * 8
+        self.in_dev = [torch.zeros(self._in_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.images = [t[:B * 784 * 4].view(torch.float32).view(B, 784) for t in self.in_dev]
+        self.labels = [t[B * 784 * 4:].view(torch.int64) for t in self.in_dev]
         self.h_images = [torch.zeros(B, 784, dtype=torch.float32).pin_memory() for _ in range(2)]
         self.h_labels = [torch.zeros(B, dtype=torch.int64).pin_memory() for _ in range(2)]
         self.x16 = torch.zeros(B, 784, dtype=bf, device=dev)
@@ -492,6 +521,8 @@ class CudaMlpEngine(ComputeEngine):
 
     # shared plumbing with the convnet engine
     load_batch = CudaLeNetEngine.load_batch
+    pack_batch = CudaLeNetEngine.pack_batch
+    load_packed = CudaLeNetEngine.load_packed
     attach_optimizer = CudaLeNetEngine.attach_optimizer
     params_updated = CudaLeNetEngine.params_updated
     _run = CudaLeNetEngine._run
@@ -565,6 +596,7 @@ class CudaMlpEngine(ComputeEngine):
                 n += 1
             self.backend.enqueue(self.params, self.grads, **self._opt_args)
             n += 1
+        self.h_loss_bufs[slot].copy_(self.d_loss_acc, non_blocking=True)     # result read-back is part of the step
         self.launches_per_step = n
 
     @torch.no_grad()

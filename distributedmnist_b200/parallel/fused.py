@@ -55,7 +55,7 @@ class FusedBackend(Backend):
         self._ctrl_bytes = self.ctrl.view(torch.uint8)
         self._off = {f: int(self.lib.dm_sync_ctrl_offset(f.encode())) for f in
                      ("epoch", "error", "accepted_steps", "dropped_steps", "last_mask", "last_count", "last_late",
-                      "global_step", "t_arrive", "t_start", "cta_counter", "t_phase")}
+                      "global_step", "t_arrive", "t_start", "cta_counter", "t_phase", "t_phase_e")}
         self.shadow: Optional[torch.Tensor] = None     # bf16 copy of the parameter arena
         self.drop_keep = 0.0
         self.drop_seed = 0
@@ -108,6 +108,11 @@ class FusedBackend(Backend):
     def read_phases(self):
         """%globaltimer stamps of the last launch: start, decided, reduced, pushed, landed, end (ns, relative)."""
         t = self._ctrl_bytes[self._off["t_phase"]:self._off["t_phase"] + 48].view(torch.int64).cpu().tolist()
+        return [x - t[0] for x in t]
+
+    def read_phases_early(self):
+        """Early-bucket kernel of the last step: start, arrived, reduced+pushed (CTA 0), all pushes out (ns, relative)."""
+        t = self._ctrl_bytes[self._off["t_phase_e"]:self._off["t_phase_e"] + 32].view(torch.int64).cpu().tolist()
         return [x - t[0] for x in t]
 
     def read_timing(self, first_step: int, last_step: int):

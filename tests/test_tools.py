@@ -80,3 +80,13 @@ def test_ps_role_exits_cleanly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "src", "mnist_distributed_train.py"), "--job_name=ps",
                         "--task_id=0"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "no parameter server" in (r.stdout + r.stderr)
+
+
+def test_no_undefined_names_in_gpu_only_code_paths():
+    """The CUDA engine / bench / multi-GPU workers cannot execute on the CPU box: a static undefined-name check keeps a
+    typo there from surfacing only inside a GPU run."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "lint_names.py")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]

@@ -49,7 +49,7 @@ fi
 if has ab; then
   # A/B switches: one short bench per entry of $AB (e.g. AB="DMNIST_CONV1_FWD=1 DMNIST_PRIO=0"), ms_per_step only
   for kv in ${AB:-}; do
-    r=$(env $kv bash -c "$(declare -f run_bench); GPUS=$GPUS; run_bench --steps 200 --warmup 10" 2>/dev/null | grep '^{' | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['e2e']['ms_per_step'], d.get('sync_phases_ns'))")
+    r=$(env $kv bash -c "$(declare -f run_bench); GPUS=$GPUS; run_bench --steps 200 --warmup 10" 2>/dev/null | grep '^{' | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['e2e']['ms_per_step'], d.get('sync_phases_ns'), d.get('sync_early_phases_ns'))")
     echo "AB $kv -> ms_per_step (device, e2e), sync phases = $r" | tee -a gpurun_out/ab.txt
   done
 fi
