@@ -414,6 +414,7 @@ int dm_conv1_fwd_tc(const void* images, const void* w, const void* bias, void* o
   static bool configured = false;
   if (!configured) {
     DM_CUDA_OK(cudaFuncSetAttribute(conv1_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C1FwSmem::TOTAL));
+    DM_CUDA_OK(cudaFuncSetAttribute(conv1_fwd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
   const long long total = (long long)B * 196;
@@ -431,6 +432,7 @@ int dm_conv1_wgrad_tc(const void* images, const void* dpool, const void* code, v
   static bool configured = false;
   if (!configured) {
     DM_CUDA_OK(cudaFuncSetAttribute(conv1_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C1WgSmem::TOTAL));
+    DM_CUDA_OK(cudaFuncSetAttribute(conv1_wgrad_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
   const long long total = (long long)B * 196;

@@ -512,7 +512,9 @@ int dm_conv2_fwd(const void* a1, const void* w_bf16, const void* bias, void* out
   static bool configured = false;
   if (!configured) {
     DM_CUDA_OK(cudaFuncSetAttribute(conv2_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwSmem::TOTAL));
+    DM_CUDA_OK(cudaFuncSetAttribute(conv2_fwd_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     DM_CUDA_OK(cudaFuncSetAttribute(conv2_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwSmem::TOTAL));
+    DM_CUDA_OK(cudaFuncSetAttribute(conv2_fwd_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
   const int tiles = 2 * B;
@@ -536,6 +538,7 @@ int dm_conv2_dgrad_dbg(const void* dy, const void* w_bf16, void* dx, int B, void
   static bool configured = false;
   if (!configured) {
     DM_CUDA_OK(cudaFuncSetAttribute(conv2_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DgSmem::TOTAL));
+    DM_CUDA_OK(cudaFuncSetAttribute(conv2_dgrad_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
   const int tiles = 2 * B;
@@ -559,8 +562,11 @@ int dm_conv2_wgrad(const void* a1, const void* dy, void* g_w, int B, void* strea
   static bool configured = false;
   if (!configured) {
     DM_CUDA_OK(cudaFuncSetAttribute(conv2_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem::TOTAL));
+    DM_CUDA_OK(cudaFuncSetAttribute(conv2_wgrad_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     DM_CUDA_OK(cudaFuncSetAttribute(conv2_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem::TOTAL));
+    DM_CUDA_OK(cudaFuncSetAttribute(conv2_wgrad_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     DM_CUDA_OK(cudaFuncSetAttribute(conv2_wgrad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem::TOTAL));
+    DM_CUDA_OK(cudaFuncSetAttribute(conv2_wgrad_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -434,13 +434,13 @@ struct BucketArgs {
 };
 
 // NR = number of replicas (compile time: the peer loop keeps 16 independent 16-byte loads in flight per thread).
-// CTAs are SMALL (128 threads, <= 128 registers: 16 K registers, no shared memory) and there is one per SM: they fit
+// CTAs are SMALL (192 threads, <= 96 registers: 18 K registers next to conv2_dgrad's 44 K, no shared memory) and there is one per SM: they fit
 // next to the tensor-core CTAs of conv2 dgrad/wgrad and conv1 wgrad, whose six warps leave the schedulers mostly idle,
 // so the exchange borrows issue slots instead of whole SMs.  (A first version used 20 full-size CTAs on reserved SMs:
 // an SM sustains only ~10 GB/s of peer traffic -- its outstanding-request budget over a ~3 us round trip -- so 20 of
 // them needed 33 us for the 2 x 3.2 MB, longer than the backward pass they were hiding under; see
 // profiles/bench_r1_call26_2gpu_bucketed.txt.)
-constexpr int EARLY_THREADS = 128;
+constexpr int EARLY_THREADS = 192;   // x 148 CTAs x 16 loads in flight: a 2-replica shard (200 k float4) is ONE pass
 template <int NR>
 __global__ void __launch_bounds__(EARLY_THREADS) fused_sync_early_kernel(SyncPeers P, SyncArgs a, BucketArgs r) {
   SyncCtrl* me = P.ctrl[a.rank];
@@ -696,6 +696,12 @@ int dm_fused_sync_sgd(void* const* ctrl, void* const* params, void* const* grads
   a.mc_params = reinterpret_cast<float*>(mc_params);
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (ctas < 1) ctas = 64;
+  static bool configured = false;
+  if (!configured) {     // every kernel of the step runs with the same L1/shared split, so CTAs of different kernels can share an SM
+    DM_CUDA_OK(cudaFuncSetAttribute(fused_sync_sgd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    DM_CUDA_OK(cudaFuncSetAttribute(fused_sync_sgd_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    configured = true;
+  }
   if (k < nranks) return (int)launch_kernel(fused_sync_sgd_kernel<true>, dim3(ctas), dim3(SYNC_THREADS), 0, stream, P, a);
   return (int)launch_kernel(fused_sync_sgd_kernel<false>, dim3(ctas), dim3(SYNC_THREADS), 0, stream, P, a);
 }
@@ -729,15 +735,15 @@ int dm_fused_sync_bucket(void* const* ctrl, void* const* params, void* const* gr
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (ctas < 1) ctas = 148;
   if (phase == 1) {
-    // The early kernel must be CO-RESIDENT with the tensor-core kernels of the backward pass, which run with the SM's
-    // L1/shared split at maximum shared memory.  A kernel that (by default) prefers the maximum-L1 split cannot share an
-    // SM with them and would only get SMs as their CTAs exit (observed: profiles/bench_r1_call27_2gpu.txt), so it asks
-    // for the same split although it uses no shared memory.
+    // The early kernel must be CO-RESIDENT with the tensor-core kernels of the backward pass.  CTAs of kernels that run
+    // with different L1/shared splits cannot share an SM (observed: the early kernel only got SMs as conv2_dgrad CTAs
+    // exited, profiles/bench_r1_call27_2gpu.txt), so EVERY kernel of the step asks for the same split (max shared).
     static bool configured = false;
     if (!configured) {
       DM_CUDA_OK(cudaFuncSetAttribute(fused_sync_early_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       DM_CUDA_OK(cudaFuncSetAttribute(fused_sync_early_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       DM_CUDA_OK(cudaFuncSetAttribute(fused_sync_early_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      DM_CUDA_OK(cudaFuncSetAttribute(fused_sync_late_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       configured = true;
     }
     if (nranks == 2) return (int)launch_kernel(fused_sync_early_kernel<2>, dim3(ctas), dim3(EARLY_THREADS), 0, stream, P, a, r);

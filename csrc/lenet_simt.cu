@@ -602,6 +602,11 @@ int dm_fc2_fwd_bwd(const void* h_part, long long part_stride, int splits, const 
   a.step_ptr = reinterpret_cast<const uint32_t*>(step_ptr);
   a.keep_prob = keep_prob;
   a.inv_batch = 1.f / (float)B;
+  static bool configured = false;
+  if (!configured) {
+    DM_CUDA_OK(cudaFuncSetAttribute(dm::fc2_fwd_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    configured = true;
+  }
   return (int)dm::launch_kernel(dm::fc2_fwd_bwd_kernel, dim3(B), dim3(dm::F2_THREADS), 0,
                                 reinterpret_cast<cudaStream_t>(stream), a);
 }

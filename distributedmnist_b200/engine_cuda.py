@@ -220,6 +220,17 @@ class CudaLeNetEngine(ComputeEngine):
             fork1 = torch.cuda.Event()
             fork1.record(main)
             self._side[0].wait_event(fork1)
+            # (loss, accuracy) are final after fc2_fwd_bwd: their copy into the slot's page-locked host buffer is a branch of
+            # the step (a memcpy node of the graph) that runs under the backward pass -- reading the result costs the host
+            # no extra call, only a wait on the step's completion event
+            self._side[2].wait_event(fork1)
+            with torch.cuda.stream(self._side[2]):
+                self.h_loss_bufs[self._slot].copy_(self.d_loss_acc, non_blocking=True)
+                if not early_sync:
+                    join3 = torch.cuda.Event()
+                    join3.record(self._side[2])
+        else:
+            self.h_loss_bufs[self._slot].copy_(self.d_loss_acc, non_blocking=True)
         with torch.cuda.stream(self._side[0] if branch else main):
             # fc1 wgrad: dW1[3136,512] = a2^T (A MN-major) * dh (B MN-major), K = batch; straight into the arena
             G.gemm_bf16_raw(self.a2, self.dh, g["fc1_weights"], 3136, 512, B, 3136, 512, 512, True, True,
@@ -257,7 +268,6 @@ class CudaLeNetEngine(ComputeEngine):
                 join1 = torch.cuda.Event()
                 join1.record(self._side[0])
             # the small fc gradients (fc2 weights/biases, fc1 biases) belong to the late bucket: their own branch
-            self._side[2].wait_event(fork1)
             with torch.cuda.stream(self._side[2]):
                 check(lib.dm_fc2_wgrad(ptr(self.h_act), ptr(self.dlogits), ptr(self.dh), ptr(g["fc2_weights"]),
                                        ptr(g["fc2_biases"]), ptr(g["fc1_biases"]), B, stream_ptr()), "fc2_wgrad")
@@ -285,8 +295,7 @@ class CudaLeNetEngine(ComputeEngine):
         if branch:
             main.wait_event(join1)
             main.wait_event(join2)
-            if early_sync:
-                main.wait_event(join3)
+            main.wait_event(join3)
         return 6 if self._fuse_unpool else 7
 
     def _zero_args(self, train: bool):
@@ -391,9 +400,6 @@ class CudaLeNetEngine(ComputeEngine):
                 n += 1
             self.backend.enqueue(self.params, self.grads, **self._opt_args)
             n += 1
-        # (loss, accuracy) of the step -> page-locked host buffer of this slot, as part of the step (a memcpy node of the
-        # graph): reading the result costs the host no extra call, only a wait on the step's completion event
-        self.h_loss_bufs[slot].copy_(self.d_loss_acc, non_blocking=True)
         self.launches_per_step = n
 
     def _run(self, with_sync: bool) -> None:
