@@ -269,7 +269,9 @@ struct C1WgSmem {
   static constexpr int TOTAL = BAR_OFF + 128 + 1024;
 };
 
-__global__ void __launch_bounds__(C1T_WG_THREADS, 1)
+// (register cap: nine warps = three on scheduler 0; at 154 registers that scheduler's 16 K file was full and no other
+//  kernel's CTA could share the SM -- see conv2_dgrad_kernel)
+__global__ void __maxnreg__(128)
 conv1_wgrad_tc_kernel(const float* __restrict__ images,          // [B,28,28]
                       const __nv_bfloat16* __restrict__ dpool,   // [B,14,14,32] gradient w.r.t. the pooled activations
                       const uint8_t* __restrict__ code,          // [B,14,14,32]

@@ -251,7 +251,11 @@ struct DgSmem {
   static constexpr int TOTAL = BAR_OFF + 512 + 1024;
 };
 
-__global__ void __launch_bounds__(CV_THREADS, 1)
+// Register cap: the register file is per scheduler (4 x 16 K).  At 230 registers/thread the two schedulers that hold two
+// of this CTA's six warps had 1.5 K registers left, so no other kernel's CTA (which needs a warp on every scheduler) could
+// share the SM: fc2_wgrad and the early aggregation kernel only started as these CTAs exited (profiles/bench_r1_call30_1gpu.txt,
+// profiles/coresidency_probe_r1.txt).  128 registers leave 8 K per scheduler.
+__global__ void __maxnreg__(128)
 conv2_dgrad_kernel(const __grid_constant__ CUtensorMap tmDY,  // dY NHWC [B,14,14,64], box (64,12,20,1), 128B swizzle
                    const __grid_constant__ CUtensorMap tmW,
                    __nv_bfloat16* __restrict__ dx,            // [B,14,14,32]

@@ -1,0 +1,80 @@
+// Probe: can CTAs of two different kernels share an SM?  (tools/gpu_probe_coresidency.py)
+//
+// The step graph relies on small kernels (fc2_wgrad, the early aggregation kernel) running NEXT TO the persistent
+// tensor-core kernels, which hold one CTA per SM for 10-15 us.  This probe launches a "resident" kernel that occupies
+// every SM with one CTA of a given shape (dynamic shared memory, registers per thread, threads) and spins, then a
+// "guest" kernel on another stream, and reports when the guest's CTAs actually started: during the residents'
+// lifetime (co-resident) or only after they exited.
+#include "common.cuh"
+#include "host_utils.h"
+
+namespace dm {
+
+template <int NREG>
+__global__ void __launch_bounds__(192, 1) probe_resident_kernel(unsigned long long ns, unsigned long long* t, float* sink) {
+  extern __shared__ uint8_t probe_smem[];
+  float r[NREG];
+#pragma unroll
+  for (int i = 0; i < NREG; ++i) r[i] = (float)(threadIdx.x * (i + 1));
+  const unsigned long long t0 = globaltimer_ns();
+  unsigned iter = 0;
+  while (globaltimer_ns() - t0 < ns) {
+#pragma unroll
+    for (int i = 0; i < NREG; ++i) r[i] = fmaf(r[i], 1.0001f, (float)iter);     // keep every value live
+    ++iter;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NREG; ++i) s += r[i];
+  if (s == 12345.678f) sink[0] = s + (float)probe_smem[0];
+  if (threadIdx.x == 0) {
+    atomicMin(&t[0], t0);
+    atomicMax(&t[1], globaltimer_ns());
+  }
+}
+
+__global__ void probe_guest_kernel(unsigned long long* t, unsigned long long ns) {
+  __shared__ float pad[64];
+  const unsigned long long t0 = globaltimer_ns();
+  pad[threadIdx.x & 63] = (float)t0;
+  while (globaltimer_ns() - t0 < ns) {
+  }
+  if (threadIdx.x == 0) {
+    atomicMin(&t[2], t0);     // first guest CTA start
+    atomicMax(&t[3], t0);     // last guest CTA start
+    atomicMax(&t[4], globaltimer_ns());
+  }
+}
+
+}  // namespace dm
+
+// out: 5 x uint64 {resident first start, resident last end, guest first start, guest last start, guest last end}
+extern "C" int dm_probe_coresidency(int res_smem, int res_regs, int res_ctas, int guest_threads, int guest_ctas, int pdl,
+                                    int prio_res, int prio_guest, int carve_res, int carve_guest, int order_guest_first,
+                                    void* out, void* sink) {
+  using namespace dm;
+  cudaStream_t sa, sb;
+  DM_CUDA_OK(cudaStreamCreateWithPriority(&sa, cudaStreamNonBlocking, prio_res));
+  DM_CUDA_OK(cudaStreamCreateWithPriority(&sb, cudaStreamNonBlocking, prio_guest));
+  unsigned long long* t = reinterpret_cast<unsigned long long*>(out);
+  unsigned long long init[5] = {~0ull, 0ull, ~0ull, 0ull, 0ull};
+  DM_CUDA_OK(cudaMemcpy(t, init, sizeof(init), cudaMemcpyHostToDevice));
+  auto res = res_regs >= 200 ? probe_resident_kernel<200> : (res_regs >= 100 ? probe_resident_kernel<90> : probe_resident_kernel<16>);
+  DM_CUDA_OK(cudaFuncSetAttribute(res, cudaFuncAttributeMaxDynamicSharedMemorySize, res_smem));
+  if (carve_res >= 0) DM_CUDA_OK(cudaFuncSetAttribute(res, cudaFuncAttributePreferredSharedMemoryCarveout, carve_res));
+  if (carve_guest >= 0) DM_CUDA_OK(cudaFuncSetAttribute(probe_guest_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve_guest));
+  const int saved = g_pdl;
+  g_pdl = pdl;
+  cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
+  if (order_guest_first) e2 = launch_kernel(probe_guest_kernel, dim3(guest_ctas), dim3(guest_threads), 0, sb, t, 20000ull);
+  e1 = launch_kernel(res, dim3(res_ctas), dim3(192), (size_t)res_smem, sa, 60000ull, t, reinterpret_cast<float*>(sink));
+  if (!order_guest_first) e2 = launch_kernel(probe_guest_kernel, dim3(guest_ctas), dim3(guest_threads), 0, sb, t, 2000ull);
+  g_pdl = saved;
+  DM_CUDA_OK(e1);
+  DM_CUDA_OK(e2);
+  DM_CUDA_OK(cudaStreamSynchronize(sa));
+  DM_CUDA_OK(cudaStreamSynchronize(sb));
+  DM_CUDA_OK(cudaStreamDestroy(sa));
+  DM_CUDA_OK(cudaStreamDestroy(sb));
+  return 0;
+}

@@ -434,13 +434,13 @@ struct BucketArgs {
 };
 
 // NR = number of replicas (compile time: the peer loop keeps 16 independent 16-byte loads in flight per thread).
-// CTAs are SMALL (192 threads, <= 96 registers: 18 K registers next to conv2_dgrad's 44 K, no shared memory) and there is one per SM: they fit
+// CTAs are SMALL (128 threads = one warp per scheduler, <= 96 registers, no shared memory) and there is one per SM: they fit
 // next to the tensor-core CTAs of conv2 dgrad/wgrad and conv1 wgrad, whose six warps leave the schedulers mostly idle,
 // so the exchange borrows issue slots instead of whole SMs.  (A first version used 20 full-size CTAs on reserved SMs:
 // an SM sustains only ~10 GB/s of peer traffic -- its outstanding-request budget over a ~3 us round trip -- so 20 of
 // them needed 33 us for the 2 x 3.2 MB, longer than the backward pass they were hiding under; see
 // profiles/bench_r1_call26_2gpu_bucketed.txt.)
-constexpr int EARLY_THREADS = 192;   // x 148 CTAs x 16 loads in flight: a 2-replica shard (200 k float4) is ONE pass
+constexpr int EARLY_THREADS = 128;   // one warp per scheduler, 3 K registers each: fits next to conv2_dgrad / conv1_wgrad CTAs
 template <int NR>
 __global__ void __launch_bounds__(EARLY_THREADS) fused_sync_early_kernel(SyncPeers P, SyncArgs a, BucketArgs r) {
   SyncCtrl* me = P.ctrl[a.rank];

@@ -90,7 +90,7 @@ class CudaLeNetEngine(ComputeEngine):
         # the data-gradient chain is the critical path: it is captured on a high-priority stream, the weight-gradient
         # side branches on low-priority ones, so the block scheduler serves the chain first whenever both have CTAs pending
         lo, hi = (0, -1)
-        self._side = [torch.cuda.Stream(device=dev, priority=lo) for _ in range(3)]
+        self._side = [torch.cuda.Stream(device=dev, priority=lo) for _ in range(4)]
         self._main_priority = hi if os.environ.get("DMNIST_PRIO", "1") != "0" else lo
         self._wgrad_late = os.environ.get("DMNIST_WGRAD_LATE", "1") != "0"
         self._branches = os.environ.get("DMNIST_BRANCHES", "1") != "0"
@@ -223,12 +223,13 @@ class CudaLeNetEngine(ComputeEngine):
             # (loss, accuracy) are final after fc2_fwd_bwd: their copy into the slot's page-locked host buffer is a branch of
             # the step (a memcpy node of the graph) that runs under the backward pass -- reading the result costs the host
             # no extra call, only a wait on the step's completion event
-            self._side[2].wait_event(fork1)
-            with torch.cuda.stream(self._side[2]):
+            # (its own branch, joined only at the very end of the step: a memcpy node in front of the aggregation kernel
+            # would cost that kernel its programmatic launch edge)
+            self._side[3].wait_event(fork1)
+            with torch.cuda.stream(self._side[3]):
                 self.h_loss_bufs[self._slot].copy_(self.d_loss_acc, non_blocking=True)
-                if not early_sync:
-                    join3 = torch.cuda.Event()
-                    join3.record(self._side[2])
+                self._join_loss = torch.cuda.Event()
+                self._join_loss.record(self._side[3])
         else:
             self.h_loss_bufs[self._slot].copy_(self.d_loss_acc, non_blocking=True)
         with torch.cuda.stream(self._side[0] if branch else main):
@@ -268,6 +269,7 @@ class CudaLeNetEngine(ComputeEngine):
                 join1 = torch.cuda.Event()
                 join1.record(self._side[0])
             # the small fc gradients (fc2 weights/biases, fc1 biases) belong to the late bucket: their own branch
+            self._side[2].wait_event(fork1)
             with torch.cuda.stream(self._side[2]):
                 check(lib.dm_fc2_wgrad(ptr(self.h_act), ptr(self.dlogits), ptr(self.dh), ptr(g["fc2_weights"]),
                                        ptr(g["fc2_biases"]), ptr(g["fc1_biases"]), B, stream_ptr()), "fc2_wgrad")
@@ -295,7 +297,8 @@ class CudaLeNetEngine(ComputeEngine):
         if branch:
             main.wait_event(join1)
             main.wait_event(join2)
-            main.wait_event(join3)
+            if early_sync:
+                main.wait_event(join3)
         return 6 if self._fuse_unpool else 7
 
     def _zero_args(self, train: bool):
@@ -400,6 +403,8 @@ class CudaLeNetEngine(ComputeEngine):
                 n += 1
             self.backend.enqueue(self.params, self.grads, **self._opt_args)
             n += 1
+        if self._branches:
+            torch.cuda.current_stream().wait_event(self._join_loss)      # the loss read-back branch rejoins at the end of the step
         self.launches_per_step = n
 
     def _run(self, with_sync: bool) -> None:

@@ -28,6 +28,22 @@ if has diag; then
   fi
 fi
 
+if has mgtests; then
+  # multi-GPU boxes are charged per GPU: only the multi-rank tests there
+  timeout 600 python -m pytest tests/test_fused_sync_gpu.py -m gpu -x -q > gpurun_out/pytest_multigpu.log 2>&1
+  echo "pytest(multi-gpu) exit=$?" >> gpurun_out/pytest_multigpu.log
+  tail -4 gpurun_out/pytest_multigpu.log
+fi
+
+if has kofn; then
+  # backup-worker configuration of BASELINE.json: K = N-2 of N with one replica delayed on the device every step
+  K=$((GPUS-2)); [ "$K" -lt 1 ] && K=1
+  run_bench --k $K --straggler $((GPUS-1)):1.0:300 --steps 200 --warmup 10 > gpurun_out/bench_kofn_$GPUS.json 2> gpurun_out/bench_kofn_$GPUS.err
+  echo "bench K=$K of $GPUS (rank $((GPUS-1)) delayed 300 us/step) exit=$?"; cat gpurun_out/bench_kofn_$GPUS.json
+  run_bench --model mlp3 --batch 8192 --hidden 4096 --steps 30 --warmup 5 > gpurun_out/bench_mlp3_$GPUS.json 2> gpurun_out/bench_mlp3_$GPUS.err
+  echo "bench mlp3 B=8192 exit=$?"; cat gpurun_out/bench_mlp3_$GPUS.json
+fi
+
 if has tests; then
   timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
   echo "pytest exit=$?" >> gpurun_out/pytest_gpu.log
@@ -57,6 +73,10 @@ fi
 if has trace; then
   run_bench --steps 20 --warmup 5 --trace gpurun_out/timeline > gpurun_out/trace_run.log 2>&1
   echo "trace exit=$?"; cat gpurun_out/timeline.txt
+fi
+
+if has probe; then
+  timeout 120 python tools/gpu_probe_coresidency.py > gpurun_out/coresidency_probe.log 2>&1; cat gpurun_out/coresidency_probe.log | cut -c1-220
 fi
 
 if has dgradtl; then
