@@ -559,7 +559,7 @@ int dm_conv2_wgrad(const void* a1, const void* dy, void* g_w, int B, void* strea
   if (make_tmap_nhwc_bf16(&tmX, a1, 32, 14, 14, B, 32, 12, 20, 64)) return 101;
   if (make_tmap_nhwc_bf16(&tmDY, dy, 64, 14, 14, B, 64, 8, 16, 128)) return 102;
   const int tiles = 2 * B;
-  static const int gpc = env_int("DMNIST_WGRAD_GPC", 2);      // tap groups per CTA: 1 (first version), 2, 4
+  static const int gpc = env_int("DMNIST_WGRAD_GPC", 1);      // tap groups per CTA: 1 (first version), 2, 4
   const int sets = gpc == 1 ? 7 : (gpc == 2 ? 4 : 2);
   int splits = g_max_ctas / sets;
   if (splits > tiles) splits = tiles;
