@@ -45,7 +45,11 @@ struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = GEMM_STAGES * STAGE_BYTES;
+  // 128-wide tiles run a 3-deep ring (97 KB): fc1_wgrad (K = batch = 4 k-blocks) then fits on an SM NEXT TO the CTA of
+  // fc1_dgrad (100 KB) instead of racing it for whole SMs -- whichever of the two ~100-CTA grids was dispatched first used
+  // to delay the other by a full kernel (4 us on the critical path when the side branch won).
+  static constexpr int STAGES = BN == 128 ? 3 : GEMM_STAGES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + alignment slack
 };
 
@@ -62,8 +66,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // 128B swizzle atoms repeat every 1024 B: align the ring so descriptors need no base offset.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
-  uint64_t* empty_bar = full_bar + GEMM_STAGES;
-  uint64_t* tmem_full_bar = empty_bar + GEMM_STAGES;
+  uint64_t* empty_bar = full_bar + S::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + S::STAGES;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -78,7 +82,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < GEMM_STAGES; ++s) {
+    for (int s = 0; s < S::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -97,8 +101,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % GEMM_STAGES;
-        const uint32_t ph = (i / GEMM_STAGES) & 1;
+        const int s = i % S::STAGES;
+        const uint32_t ph = (i / S::STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* sA = smem + s * S::STAGE_BYTES;
         uint8_t* sB = sA + S::A_BYTES;
@@ -122,8 +126,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------ MMA issuer --------------------------------
     constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, A_MN, B_MN);
     for (int i = 0; i < nkb; ++i) {
-      const int s = i % GEMM_STAGES;
-      const uint32_t ph = (i / GEMM_STAGES) & 1;
+      const int s = i % S::STAGES;
+      const uint32_t ph = (i / S::STAGES) & 1;
       mbar_wait(&full_bar[s], ph);
       tc_fence_after_sync();
       if (elect_one()) {
