@@ -45,10 +45,9 @@ struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // 128-wide tiles run a 3-deep ring (97 KB): fc1_wgrad (K = batch = 4 k-blocks) then fits on an SM NEXT TO the CTA of
-  // fc1_dgrad (100 KB) instead of racing it for whole SMs -- whichever of the two ~100-CTA grids was dispatched first used
-  // to delay the other by a full kernel (4 us on the critical path when the side branch won).
-  static constexpr int STAGES = BN == 128 ? 3 : GEMM_STAGES;
+  // (a 3-deep ring for the 128-wide tiles would let fc1_wgrad share SMs with fc1_dgrad; measured: both then take 12 us
+  //  instead of 9.4 + 7.8 back to back and the critical path loses 3 us -- profiles/bench_r1_call35_1gpu.txt -- so 4 it is)
+  static constexpr int STAGES = GEMM_STAGES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + alignment slack
 };

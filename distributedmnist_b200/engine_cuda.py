@@ -232,6 +232,18 @@ class CudaLeNetEngine(ComputeEngine):
                 self._join_loss.record(self._side[3])
         else:
             self.h_loss_bufs[self._slot].copy_(self.d_loss_acc, non_blocking=True)
+        sp = stream_ptr()
+        # fc1 dgrad: dxfc[B,3136] = dh[B,512] (K-major) * W1[3136,512] (rows = in, K = out contiguous)
+        if self._fuse_unpool:
+            # ... with maxpool2/ReLU2 backward and the conv2 bias gradient in the GEMM epilogue (no [B,3136] intermediate)
+            check(lib.dm_fc1_dgrad_unpool(ptr(self.dh), ptr(pb["fc1_weights"]), ptr(self.code2), ptr(self.dy2),
+                                          ptr(g["conv2_biases"]), B, sp), "fc1_dgrad_unpool")
+        else:
+            G.gemm_bf16_raw(self.dh, pb["fc1_weights"], self.dxfc, B, 3136, 512, 512, 512, 3136, False, False,
+                            G.EPI_STORE_BF16, bn=64)
+            check(lib.dm_unpool2(ptr(self.dxfc), ptr(self.code2), ptr(self.dy2), ptr(g["conv2_biases"]), B, sp), "unpool2")
+        # (the side branch is issued AFTER the chain's kernel: both become ready together and the first one dispatched takes
+        #  the SMs -- the data-gradient GEMM must be that one)
         with torch.cuda.stream(self._side[0] if branch else main):
             # fc1 wgrad: dW1[3136,512] = a2^T (A MN-major) * dh (B MN-major), K = batch; straight into the arena
             G.gemm_bf16_raw(self.a2, self.dh, g["fc1_weights"], 3136, 512, B, 3136, 512, 512, True, True,
@@ -243,16 +255,6 @@ class CudaLeNetEngine(ComputeEngine):
             if branch and not early_sync:
                 join1 = torch.cuda.Event()
                 join1.record(self._side[0])
-        sp = stream_ptr()
-        # fc1 dgrad: dxfc[B,3136] = dh[B,512] (K-major) * W1[3136,512] (rows = in, K = out contiguous)
-        if self._fuse_unpool:
-            # ... with maxpool2/ReLU2 backward and the conv2 bias gradient in the GEMM epilogue (no [B,3136] intermediate)
-            check(lib.dm_fc1_dgrad_unpool(ptr(self.dh), ptr(pb["fc1_weights"]), ptr(self.code2), ptr(self.dy2),
-                                          ptr(g["conv2_biases"]), B, sp), "fc1_dgrad_unpool")
-        else:
-            G.gemm_bf16_raw(self.dh, pb["fc1_weights"], self.dxfc, B, 3136, 512, 512, 512, 3136, False, False,
-                            G.EPI_STORE_BF16, bn=64)
-            check(lib.dm_unpool2(ptr(self.dxfc), ptr(self.code2), ptr(self.dy2), ptr(g["conv2_biases"]), B, sp), "unpool2")
         if early_sync:
             # early bucket: every fc gradient is final once fc1_wgrad / fc2_wgrad are done; the kernel also rewrites my
             # shard of the fc1 bf16 shadow, which fc1_dgrad (just launched on the main stream) still reads -> order after it

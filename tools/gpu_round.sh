@@ -35,13 +35,15 @@ if has mgtests; then
   tail -4 gpurun_out/pytest_multigpu.log
 fi
 
-if has kofn; then
+if has kofn; then  # (mlp3 only when MLP3=1)
   # backup-worker configuration of BASELINE.json: K = N-2 of N with one replica delayed on the device every step
   K=$((GPUS-2)); [ "$K" -lt 1 ] && K=1
   run_bench --k $K --straggler $((GPUS-1)):1.0:300 --steps 200 --warmup 10 > gpurun_out/bench_kofn_$GPUS.json 2> gpurun_out/bench_kofn_$GPUS.err
   echo "bench K=$K of $GPUS (rank $((GPUS-1)) delayed 300 us/step) exit=$?"; cat gpurun_out/bench_kofn_$GPUS.json
-  run_bench --model mlp3 --batch 8192 --hidden 4096 --steps 30 --warmup 5 > gpurun_out/bench_mlp3_$GPUS.json 2> gpurun_out/bench_mlp3_$GPUS.err
-  echo "bench mlp3 B=8192 exit=$?"; cat gpurun_out/bench_mlp3_$GPUS.json
+  if [ "${MLP3:-0}" = "1" ]; then
+    run_bench --model mlp3 --batch 8192 --hidden 4096 --steps 30 --warmup 5 > gpurun_out/bench_mlp3_$GPUS.json 2> gpurun_out/bench_mlp3_$GPUS.err
+    echo "bench mlp3 B=8192 exit=$?"; cat gpurun_out/bench_mlp3_$GPUS.json
+  fi
 fi
 
 if has tests; then
@@ -73,6 +75,15 @@ fi
 if has trace; then
   run_bench --steps 20 --warmup 5 --trace gpurun_out/timeline > gpurun_out/trace_run.log 2>&1
   echo "trace exit=$?"; cat gpurun_out/timeline.txt
+fi
+
+if has sanitize; then
+  # compute-sanitizer over the kernel numerics checks (the reference has no race/memory checking at all)
+  for tool in memcheck racecheck; do
+    timeout 300 compute-sanitizer --tool $tool --print-limit 20 python tools/gpu_diag_lenet.py ${SAN:-conv1 fc2_loss fc1_dgrad conv2_fwd} \
+        > gpurun_out/sanitizer_$tool.log 2>&1
+    echo "compute-sanitizer $tool exit=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|Error|hazard" gpurun_out/sanitizer_$tool.log | head -8
+  done
 fi
 
 if has probe; then
