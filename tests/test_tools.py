@@ -90,3 +90,24 @@ def test_no_undefined_names_in_gpu_only_code_paths():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "lint_names.py")], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-3000:]
+
+
+def test_transfer_client_put_get_recursive(tmp_path):
+    """tools/transfer.py: the one-box counterpart of the reference's vendored SCP client (tools/scp.py put :122 / get :158)."""
+    from transfer import TransferClient, TransferError
+    src = tmp_path / "run" / "train_dir"
+    os.makedirs(src / "sub")
+    (src / "checkpoint").write_text('model_checkpoint_path: "model.ckpt-7"\n')
+    (src / "sub" / "out_master").write_bytes(b"x" * 300000)
+    seen = []
+    c = TransferClient(progress=lambda name, size, sent: seen.append((name, size, sent)), buff_size=1 << 16)
+    c.get(str(src), str(tmp_path / "dl"), recursive=True)
+    assert (tmp_path / "dl" / "checkpoint").read_text().startswith("model_checkpoint_path")
+    assert (tmp_path / "dl" / "sub" / "out_master").stat().st_size == 300000
+    assert seen and seen[-1][1] == seen[-1][2]                      # progress callback reaches 100 %
+    c.put([str(src / "checkpoint")], str(tmp_path / "up.txt"))
+    assert (tmp_path / "up.txt").exists()
+    with pytest.raises(TransferError):
+        c.get(str(src), str(tmp_path / "nope"))                     # directory without recursive=True
+    with pytest.raises(TransferError):
+        c.get(str(tmp_path / "missing"), str(tmp_path / "x"))

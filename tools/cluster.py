@@ -46,6 +46,9 @@ if ROOT not in sys.path:
 
 from distributedmnist_b200.parallel.launcher import free_port  # noqa: E402
 
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from transfer import TransferClient  # noqa: E402  (counterpart of the reference's vendored tools/scp.py)
+
 
 class Cfg(dict):
     """Dict whose string values (and lists of strings) are ``%``-interpolated against the dict itself."""
@@ -274,7 +277,7 @@ def download_file(argv, configuration: Cfg):
     os.makedirs(outdir, exist_ok=True)
     src = os.path.join(configuration["base_out_dir"], fname)
     dst = os.path.join(outdir, "%s_%s" % (configuration["name"], os.path.basename(fname)))
-    shutil.copyfile(src, dst)
+    TransferClient().get(src, dst)
     return dst
 
 
@@ -283,7 +286,7 @@ def download_outdir(argv, configuration: Cfg):
     dst = os.path.join(outdir, configuration["name"])
     if os.path.exists(dst):
         shutil.rmtree(dst)
-    shutil.copytree(configuration["base_out_dir"], dst)
+    TransferClient().get(configuration["base_out_dir"], dst, recursive=True)
     return dst
 
 
