@@ -178,7 +178,8 @@ def main():
         return 1
     n, rank, B = ctx.world_size, ctx.rank, args.batch
     k = n if args.k < 0 else args.k
-    backend = FusedBackend(ctx)
+    # backup-worker runs: a short watchdog so a starved replica can cost seconds, never minutes
+    backend = FusedBackend(ctx) if k == n else FusedBackend(ctx, timeout_ms=5000.0)
     if args.model == "lenet":
         engine = CudaLeNetEngine(B, backend, seed=66478, rank=rank, use_graph=not args.no_graph)
     else:
@@ -220,6 +221,36 @@ def main():
         engine.train_step()                                   # the step's last graph node copies (loss, acc) to pinned host memory
         return engine.read_loss_async()                       # (completion event, host buffer): read one step later
 
+    def run_global_steps(step_fn, steps: int) -> int:
+        """K < N (backup workers, reference SyncReplicasOptimizer): replicas are NOT in lock step -- a delayed replica's
+        gradient is dropped and it fast-forwards -- so a fixed number of LOCAL iterations per replica would leave the
+        slowest one alone at the end, waiting for arrivals that never come.  Everyone instead free-runs until the GLOBAL
+        step has advanced by ``steps`` (the device epoch is polled every 8 iterations; before every launch once the target is
+        near or once this replica has been seen fast-forwarding -- so nobody launches a step at or beyond the target).  Returns the number of images whose
+        gradients were accepted across all replicas."""
+        ep = torch.tensor([backend.device_epoch], device=ctx.device, dtype=torch.int64)
+        if n > 1:
+            dist.broadcast(ep, src=0)                        # the chief's view defines the window for everybody
+        target = int(ep.item()) + steps
+        acc0 = backend._read_u32("accepted_steps")
+        it, since, careful, known = 0, 0, False, backend.device_epoch
+        while True:
+            if careful or since >= 8 or known + since >= target - 16:
+                now = backend.device_epoch                   # synchronises this replica's stream
+                if now - known > since:
+                    careful = True       # fast-forwarded past steps it did not take part in: a straggler checks before EVERY launch
+                known, since = now, 0
+            if known >= target:
+                break
+            step_fn(it)
+            it += 1
+            since += 1
+        torch.cuda.synchronize()
+        accepted = torch.tensor([backend._read_u32("accepted_steps") - acc0], device=ctx.device, dtype=torch.int64)
+        if n > 1:
+            dist.all_reduce(accepted)
+        return int(accepted.item()) * B
+
     # ---- warm-up (captures the graphs) ------------------------------------------------------------------------
     for i in range(max(args.warmup, 3)):
         device_step(i)
@@ -231,8 +262,12 @@ def main():
     sampler.start()
     barrier()
     e0.record()
-    for i in range(args.steps):
-        device_step(i)
+    if k == n:
+        for i in range(args.steps):
+            device_step(i)
+        images_dev = n * B * args.steps
+    else:
+        images_dev = run_global_steps(device_step, args.steps)
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -249,14 +284,23 @@ def main():
     e0.record()
     pending = None
     last_loss = 0.0
-    for i in range(args.steps):
-        ev = e2e_step(i)
-        if pending is not None:
-            pending[0].synchronize()
-            last_loss = float(pending[1][0])                  # the step's result is consumed on the host
-        pending = ev
-    pending[0].synchronize()
-    last_loss = float(pending[1][0])
+    if k == n:
+        for i in range(args.steps):
+            ev = e2e_step(i)
+            if pending is not None:
+                pending[0].synchronize()
+                last_loss = float(pending[1][0])                  # the step's result is consumed on the host
+            pending = ev
+        pending[0].synchronize()
+        last_loss = float(pending[1][0])
+        images_e2e = n * B * args.steps
+    else:
+        def e2e_consume(i):
+            nonlocal last_loss
+            ev = e2e_step(i)
+            ev[0].synchronize()
+            last_loss = float(ev[1][0])
+        images_e2e = run_global_steps(e2e_consume, args.steps)
     e1.record()
     barrier()
     ms2 = torch.tensor([e0.elapsed_time(e1)], device=ctx.device)
@@ -275,8 +319,8 @@ def main():
         write_timeline(args.trace, device_step, barrier, rank)
 
     if rank == 0:
-        value = n * B * args.steps / (ms_total / 1e3)
-        e2e_value = n * B * args.steps / (ms2_total / 1e3)
+        value = images_dev / (ms_total / 1e3)
+        e2e_value = images_e2e / (ms2_total / 1e3)
         out = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": n, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -296,6 +340,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms2_total / args.steps,
                     "h2d_bytes_per_step": engine.h2d_bytes_per_step(), "d2h_bytes_per_step": 8,
                     "last_loss": last_loss},
+            "backup_workers": (None if k == n else
+                               {"k": k, "n": n, "window_global_steps": args.steps, "accepted_images_device_phase": images_dev,
+                                "note": "replicas free-run until the global step advanced by `steps`; value = accepted images / time"}),
             "gpu_launches": launches, "gpu_launches_per_step": engine.launches_per_step,
             "final_global_step": info.global_step,
             "sync_phases_ns": dict(zip(["start", "decided", "reduced", "pushed", "landed", "end"], backend.read_phases())),
