@@ -5,6 +5,7 @@ replica (allocated through the aggregation backend so that, on the GPU path,
 both live in NVLink-symmetric memory) and exposes four calls:
 
 * ``load_batch(images, labels)``  -- host (pinned) -> device copy of the step's inputs
+  (``pack_batch`` / ``load_packed``: the same with one contiguous buffer and one copy per step)
 * ``forward_backward(step)``      -- loss, train accuracy and all gradients
 * ``loss_acc()``                  -- device -> host read of the step's scalars
 * ``evaluate(images, labels)``    -- inference-only loss/accuracy (evaluator)
@@ -47,6 +48,22 @@ class ComputeEngine:
 
     def h2d_bytes_per_step(self) -> int:
         raise NotImplementedError
+
+    # ---- packed batches: one contiguous buffer per step (fp32 images [B,784] then int64 labels [B]) -----------------
+    def pack_batch(self, images, labels, pin: bool = True) -> torch.Tensor:
+        """Input pipelines fill one (page-locked) buffer per batch; ``load_packed`` then moves it with a single copy
+        (the sm_100a engines keep images and labels of a slot in one device allocation for exactly this)."""
+        B = self.batch_size
+        buf = torch.empty(B * 784 * 4 + B * 8, dtype=torch.uint8)
+        if pin and torch.cuda.is_available():
+            buf = buf.pin_memory()
+        buf[:B * 784 * 4].view(torch.float32).copy_(torch.as_tensor(images, dtype=torch.float32).reshape(B * 784))
+        buf[B * 784 * 4:].view(torch.int64).copy_(torch.as_tensor(labels, dtype=torch.int64).reshape(B))
+        return buf
+
+    def load_packed(self, packed: torch.Tensor) -> None:
+        B = self.batch_size
+        self.load_batch(packed[:B * 784 * 4].view(torch.float32).view(B, 28, 28, 1), packed[B * 784 * 4:].view(torch.int64))
 
 
 class TorchEngine(ComputeEngine):

@@ -155,3 +155,95 @@ class StoreCommitBoard:
                 self.store.delete_key(key)
             except Exception:
                 pass
+
+
+class BucketedExchange:
+    """Executable specification of the bucketed, overlapped aggregation of ``csrc/fused_sync.cu`` (K == N).
+
+    Threads play the replicas, numpy arrays the symmetric arenas, integer flag words (value = epoch + 1, monotonic) the
+    control block.  ``early(rank)`` / ``late(rank)`` do exactly what ``fused_sync_early_kernel`` /
+    ``fused_sync_late_kernel`` do, in the same order:
+
+    * early: arrive_e all-to-all -> reduce my shard of the early bucket over every replica's gradient arena -> SGD ->
+      store the new weights into EVERY replica's parameter arena -> done_e flags.  Does not wait for the peers' pushes.
+    * late: arrive all-to-all -> one-shot: sum all contributions of the late ranges in rank order, update the local
+      parameters only -> done flags (my reads of the peers' gradient arenas are complete) -> wait done_e of every peer
+      (their early pushes have landed here) -> wait done of every peer (nobody still reads MY gradient arena, which the
+      next step overwrites) -> epoch + 1.
+
+    The model checks the two hazards the waits exist for: a reader must never see a gradient arena of another step
+    (``grad_step``), and nobody may write a parameter range its owner still reads in the same step (``busy_early``).
+    """
+
+    def __init__(self, n: int, numel: int, early_range, lr: float = 0.1):
+        import numpy as np
+        self.np, self.n, self.numel, self.lr = np, n, numel, lr
+        self.e0, self.e1 = early_range
+        rng = np.random.default_rng(0)
+        w0 = rng.standard_normal(numel).astype(np.float32)
+        self.params = [w0.copy() for _ in range(n)]
+        self.grads = [np.zeros(numel, np.float32) for _ in range(n)]
+        self.grad_step = [-1] * n              # which step's gradients arena r currently holds
+        self.busy_early = [False] * n          # replica r's compute still reads its early-range parameters
+        self.early_from = [[-1] * n for _ in range(n)]   # [r][q]: step of the last early-bucket shard replica q pushed into r
+        self.epoch = [0] * n
+        self.arrive_e = [[0] * n for _ in range(n)]   # [owner][peer]
+        self.done_e = [[0] * n for _ in range(n)]
+        self.arrive = [[0] * n for _ in range(n)]
+        self.done = [[0] * n for _ in range(n)]
+        self._cv = threading.Condition()
+
+    def _post(self, table, me: int, value: int) -> None:
+        with self._cv:
+            for q in range(self.n):
+                table[q][me] = value
+            self._cv.notify_all()
+
+    def _wait(self, row, value: int, timeout: float = 10.0) -> None:
+        end = time.monotonic() + timeout
+        with self._cv:
+            while not all(v >= value for v in row):
+                left = end - time.monotonic()
+                if left <= 0:
+                    raise TimeoutError("flag wait timed out: %s < %d" % (row, value))
+                self._cv.wait(left)
+
+    def write_grads(self, r: int, g) -> None:
+        """The backward pass of replica r overwrites its gradient arena for its current step."""
+        self.grads[r][:] = g
+        self.grad_step[r] = self.epoch[r]
+
+    def early(self, r: int) -> None:
+        np, n, ep = self.np, self.n, self.epoch[r]
+        self._post(self.arrive_e, r, ep + 1)
+        self._wait(self.arrive_e[r], ep + 1)
+        size = self.e1 - self.e0
+        shard = (size + n - 1) // n
+        b, e = self.e0 + r * shard, min(self.e0 + (r + 1) * shard, self.e1)
+        acc = np.zeros(max(e - b, 0), np.float32)
+        for q in range(n):                                    # rank order: the same sum on every implementation
+            assert self.grad_step[q] == ep, "replica %d read replica %d's gradients of step %d in step %d" % (r, q, self.grad_step[q], ep)
+            acc += self.grads[q][b:e]
+        nw = self.params[r][b:e] - np.float32(self.lr / n) * acc
+        for q in range(n):
+            assert not self.busy_early[q], "push into replica %d's early range while its compute still reads it" % q
+            self.params[q][b:e] = nw
+            self.early_from[q][r] = ep
+        self._post(self.done_e, r, ep + 1)
+
+    def late(self, r: int) -> None:
+        np, n, ep = self.np, self.n, self.epoch[r]
+        self._post(self.arrive, r, ep + 1)
+        self._wait(self.arrive[r], ep + 1)
+        for (b, e) in ((0, self.e0), (self.e1, self.numel)):
+            acc = np.zeros(e - b, np.float32)
+            for q in range(n):
+                assert self.grad_step[q] == ep, "replica %d read replica %d's late gradients of step %d in step %d" % (r, q, self.grad_step[q], ep)
+                acc += self.grads[q][b:e]
+            self.params[r][b:e] -= np.float32(self.lr / n) * acc
+        self._post(self.done, r, ep + 1)
+        self._wait(self.done_e[r], ep + 1)
+        # (the bf16 shadow refresh and the next forward pass read the early range from here on: every shard must be this step's)
+        assert all(v == ep for v in self.early_from[r]), "replica %d reads early-bucket shards of steps %s in step %d" % (r, self.early_from[r], ep)
+        self._wait(self.done[r], ep + 1)
+        self.epoch[r] = ep + 1

@@ -95,3 +95,22 @@ def test_checkpoint_shape_mismatch_rejected(tmp_path):
     state, _ = Saver.restore(Saver.latest(str(tmp_path)))
     with pytest.raises((ValueError, KeyError)):
         spec.from_state_dict(state)
+
+
+def test_packed_batches_round_trip_through_the_engine_api():
+    """pack_batch / load_packed (one buffer, one copy per step) feed the engine the same batch as load_batch."""
+    import torch
+
+    from distributedmnist_b200.engine import TorchEngine
+    eng = TorchEngine("lenet", 8, torch.device("cpu"), lambda n: torch.zeros(n))
+    g = torch.Generator().manual_seed(3)
+    x, y = torch.rand(8, 28, 28, 1, generator=g) - 0.5, torch.randint(0, 10, (8,), generator=g)
+    eng.load_batch(x, y)
+    eng.forward_backward(0)
+    ref_loss, ref_grads = eng.loss_acc()[0], eng.grads.clone()
+    packed = eng.pack_batch(x, y, pin=False)
+    assert packed.dtype == torch.uint8 and packed.numel() == 8 * 784 * 4 + 8 * 8
+    eng.grads.zero_()
+    eng.load_packed(packed)
+    eng.forward_backward(0)
+    assert abs(eng.loss_acc()[0] - ref_loss) < 1e-7 and torch.equal(eng.grads, ref_grads)

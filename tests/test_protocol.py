@@ -95,3 +95,48 @@ def test_many_steps_many_threads_consistent():
         m = board.commit_mask(s)
         assert popcount(m) >= k
         assert all(accepted[r][s] == bool(m >> r & 1) for r in range(n) if accepted[r][s])
+
+
+def test_bucketed_overlapped_exchange_model_is_race_free_and_matches_allreduce_sgd():
+    """Host model of the bucketed aggregation (csrc/fused_sync.cu): replicas drift apart by random amounts between the
+    phases of a step; the flag waits must keep every reader on the right step's gradients, and the result must equal
+    plain allreduce -> /N -> SGD on every replica."""
+    import random
+
+    import numpy as np
+
+    from distributedmnist_b200.parallel.protocol import BucketedExchange
+    n, numel, steps = 4, 4096, 12
+    ex = BucketedExchange(n, numel, (512, 3584), lr=0.1)
+    w_ref = ex.params[0].copy()
+    all_g = [[np.random.default_rng(100 * s + r).standard_normal(numel).astype(np.float32) for r in range(n)] for s in range(steps)]
+    errors = []
+
+    def replica(r):
+        rnd = random.Random(r)
+        try:
+            for s in range(steps):
+                time.sleep(rnd.random() * 0.004)            # forward
+                ex.busy_early[r] = True                      # fc kernels read the early-range weights ...
+                time.sleep(rnd.random() * 0.002)
+                ex.write_grads(r, all_g[s][r])               # backward (overwrites the arena the peers read LAST step)
+                ex.busy_early[r] = False                     # ... until fc1_dgrad is done; only then the early kernel starts
+                ex.early(r)
+                time.sleep(rnd.random() * 0.004)            # the rest of the backward pass runs next to the early exchange
+                ex.late(r)
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=replica, args=(r,)) for r in range(n)]
+    [t.start() for t in ts]
+    [t.join(60) for t in ts]
+    assert not errors, errors
+    for s in range(steps):
+        acc = np.zeros(numel, np.float32)
+        for r in range(n):
+            acc += all_g[s][r]
+        w_ref = w_ref - np.float32(0.1 / n) * acc
+    for r in range(n):
+        assert ex.epoch[r] == steps
+        assert np.array_equal(ex.params[r], ex.params[0])           # replicas bit-identical
+    assert np.allclose(ex.params[0], w_ref, atol=1e-5)
