@@ -210,9 +210,10 @@ class CudaLeNetEngine(ComputeEngine):
         return 4
 
     def _launch_backward(self, images: torch.Tensor, B: int, early_sync: bool = False) -> int:
-        """Backward as a small DAG: the two weight-gradient GEMMs have no consumer before the aggregation
-        kernel, so they run on side streams (captured as parallel graph branches) next to the data-gradient
-        chain fc1_dgrad -> unpool2 -> conv2_dgrad -> conv1_wgrad."""
+        """Backward as a small DAG: the weight-gradient kernels have no consumer before the aggregation, so they run
+        on low-priority side streams (captured as parallel graph branches) next to the data-gradient chain
+        fc1_dgrad(+unpool) -> conv2_dgrad -> conv1_wgrad.  ``early_sync``: bucketed aggregation -- the early-bucket
+        kernel joins the fc1_wgrad branch and the small fc gradients get a branch of their own."""
         lib, g, pb = self.lib, self.g, self.pb
         main = torch.cuda.current_stream()
         branch = self._branches
@@ -256,8 +257,8 @@ class CudaLeNetEngine(ComputeEngine):
                 join1 = torch.cuda.Event()
                 join1.record(self._side[0])
         if early_sync:
-            # early bucket: every fc gradient is final once fc1_wgrad / fc2_wgrad are done; the kernel also rewrites my
-            # shard of the fc1 bf16 shadow, which fc1_dgrad (just launched on the main stream) still reads -> order after it
+            # early bucket (fc1 weights): final once fc1_wgrad is done; the kernel also rewrites my shard of the fc1 bf16
+            # shadow, which fc1_dgrad (launched above on the main stream) still reads -> ordered after it
             ev_du = torch.cuda.Event()
             ev_du.record(main)
             with torch.cuda.stream(self._side[0]):
