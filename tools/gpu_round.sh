@@ -35,17 +35,6 @@ if has mgtests; then
   tail -4 gpurun_out/pytest_multigpu.log
 fi
 
-if has kofn; then  # (mlp3 only when MLP3=1)
-  # backup-worker configuration of BASELINE.json: K = N-2 of N with one replica delayed on the device every step
-  K=$((GPUS-2)); [ "$K" -lt 1 ] && K=1
-  run_bench --k $K --straggler $((GPUS-1)):1.0:300 --steps 200 --warmup 10 > gpurun_out/bench_kofn_$GPUS.json 2> gpurun_out/bench_kofn_$GPUS.err
-  echo "bench K=$K of $GPUS (rank $((GPUS-1)) delayed 300 us/step) exit=$?"; cat gpurun_out/bench_kofn_$GPUS.json
-  if [ "${MLP3:-0}" = "1" ]; then
-    run_bench --model mlp3 --batch 8192 --hidden 4096 --steps 30 --warmup 5 > gpurun_out/bench_mlp3_$GPUS.json 2> gpurun_out/bench_mlp3_$GPUS.err
-    echo "bench mlp3 B=8192 exit=$?"; cat gpurun_out/bench_mlp3_$GPUS.json
-  fi
-fi
-
 if has tests; then
   timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
   echo "pytest exit=$?" >> gpurun_out/pytest_gpu.log
@@ -62,6 +51,17 @@ if has bench; then
   echo "bench torch exit=$?"; cat gpurun_out/bench_torch_$GPUS.json
   timeout 300 python bench.py --impl reference --gpus 1 > gpurun_out/bench_ref_1.json 2>&1
   kill $SMI
+fi
+
+if has kofn; then  # (mlp3 only when MLP3=1)
+  # backup-worker configuration of BASELINE.json: K = N-2 of N with one replica delayed on the device every step
+  K=$((GPUS-2)); [ "$K" -lt 1 ] && K=1
+  run_bench --k $K --straggler $((GPUS-1)):1.0:300 --steps 200 --warmup 10 > gpurun_out/bench_kofn_$GPUS.json 2> gpurun_out/bench_kofn_$GPUS.err
+  echo "bench K=$K of $GPUS (rank $((GPUS-1)) delayed 300 us/step) exit=$?"; cat gpurun_out/bench_kofn_$GPUS.json
+  if [ "${MLP3:-0}" = "1" ]; then
+    run_bench --model mlp3 --batch 8192 --hidden 4096 --steps 30 --warmup 5 > gpurun_out/bench_mlp3_$GPUS.json 2> gpurun_out/bench_mlp3_$GPUS.err
+    echo "bench mlp3 B=8192 exit=$?"; cat gpurun_out/bench_mlp3_$GPUS.json
+  fi
 fi
 
 if has ab; then
