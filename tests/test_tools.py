@@ -111,3 +111,20 @@ def test_transfer_client_put_get_recursive(tmp_path):
         c.get(str(src), str(tmp_path / "nope"))                     # directory without recursive=True
     with pytest.raises(TransferError):
         c.get(str(tmp_path / "missing"), str(tmp_path / "x"))
+
+
+def test_benchmark_scrapers_match_the_reference_log_formats(tmp_path):
+    import benchmark
+    log = tmp_path / "out_master"
+    log.write_text(
+        "Worker 0: 2026-09-21 08:00:00.000000: step 7, loss = 2.301234, train_acc = 0.125000, test_acc = 0.000000(1234.5 examples/sec; 0.104  sec/batch)\n"
+        "INFO ELAPSED TIMES [(0.011, 0, 10), (0.012, 1, 10), (0.031, 2, 10), (0.010, 0, 11)]\n"
+        "INFO ITERATION TIMES [0.05, 0.06]\n"
+        "Worker 0: 2026-09-21 08:00:01.000000: step 12, loss = 2.100000, train_acc = 0.250000, test_acc = 0.000000(1300.0 examples/sec; 0.098  sec/batch)\n")
+    assert benchmark.current_iteration(str(log)) == 12
+    ct = benchmark.extract_compute_times(str(log))
+    assert len(ct) == 4 and ct[2] == (0.031, 2, 10)
+    assert [w for _, w, _ in benchmark.extract_compute_times_no_master(str(log))] == [1, 2]
+    assert benchmark.extract_iteration_times(str(log)) == [0.05, 0.06]
+    stats = benchmark.worker_time_stats(ct)
+    assert stats and abs(stats["max"] - 0.031) < 1e-9

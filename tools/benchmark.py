@@ -59,6 +59,22 @@ def current_iteration(path: str) -> int:
     return cur
 
 
+def shutdown_and_launch(cfg: Cfg) -> None:
+    """reference tools/benchmark.py:17-22: tear the fleet down and bring a fresh one up.  On one box that is: stop every
+    role of the configuration, then ``launch`` (creates the run directory -- the stand-in for the NFS mount)."""
+    cluster_run(["cluster.py", "shutdown"], cfg)
+    cluster_run(["cluster.py", "launch"], cfg)
+
+
+def check_if_reached_iters(cluster_string: str, n_iters: int, cfg: Cfg, master_file_name: str = "out_master",
+                           outdir: str = "/tmp/") -> bool:
+    """reference :24-34: fetch the master's log and report whether it has passed ``n_iters`` global steps."""
+    fname = cluster_run(["cluster.py", "download_file", cluster_string, master_file_name, outdir], cfg)
+    cur = current_iteration(fname)
+    print("Currently on iteration %d" % cur)
+    return cur > n_iters
+
+
 def run_tf_and_download_files(n_iters: int, cfg: Cfg, evaluator_file_name: str = "out_evaluator",
                               master_file_name: str = "out_master", outdir: str = "result_dir",
                               timeout_s: float = 3600.0, poll_s: float = 1.0) -> Dict:
@@ -111,6 +127,12 @@ def extract_compute_times(fname: str) -> List[Tuple[float, int, int]]:
             if m:
                 out = ast.literal_eval(m.group(1))
     return out
+
+
+def extract_compute_times_no_master(fname: str, exclude_workers: Sequence[int] = (0,)) -> List[Tuple[float, int, int]]:
+    """reference :124-133 drops two hard-wired worker ids (14 and 25, the master-class machines of that fleet) from the
+    compute-time sample; here the excluded replicas are a parameter (default: the chief, which also checkpoints)."""
+    return [x for x in extract_compute_times(fname) if x[1] not in set(exclude_workers)]
 
 
 def extract_iteration_times(fname: str) -> List[float]:
