@@ -46,6 +46,8 @@ def parse_args():
                     help="lenet = the headline config; mlp3 at --batch 8192 = BASELINE.json large-message config")
     ap.add_argument("--hidden", type=int, default=4096, help="MLP hidden width")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--graphed", action="store_true", help="--impl torch_ddp: capture the whole baseline step (incl. the NCCL "
+                                                           "all-reduce) in a CUDA graph")
     ap.add_argument("--straggler", default="", help="rank:prob:usec device-side delay injection")
     ap.add_argument("--kernel-times", action="store_true", help="also print per-kernel device times (stderr)")
     ap.add_argument("--trace", default="", help="after the timed runs: CUPTI timeline (torch.profiler) of a few graph-replayed "
@@ -213,13 +215,12 @@ def main():
     def device_step(i: int):
         # inputs come from the device pool (cold in L2) through the same public call as the e2e path: the copy into the
         # slot buffer runs on the engine's copy stream and overlaps the previous step
-        engine.load_packed(d_pool[i % pool_n])
-        engine.train_step()
+        engine.step_packed(d_pool[i % pool_n])
 
     def e2e_step(i: int):
-        engine.load_packed(h_pool[i % n_host])                # pinned host -> device, one DMA on the copy stream
-        engine.train_step()                                   # the step's last graph node copies (loss, acc) to pinned host memory
-        return engine.read_loss_async()                       # (completion event, host buffer): read one step later
+        # pinned host -> device (one DMA on the copy stream) + the step graph (which copies (loss, acc) to pinned host memory)
+        # through the engine's public one-call step; returns (completion event, host loss buffer, seq): read one step later
+        return engine.step_packed(h_pool[i % n_host])
 
     def run_global_steps(step_fn, steps: int) -> int:
         """K < N (backup workers, reference SyncReplicasOptimizer): replicas are NOT in lock step -- a delayed replica's
@@ -234,7 +235,14 @@ def main():
         target = int(ep.item()) + steps
         acc0 = backend._read_u32("accepted_steps")
         it, since, careful, known = 0, 0, False, backend.device_epoch
+        t_abort = time.monotonic() + float(os.environ.get("DMNIST_BENCH_ABORT_S", "120"))
         while True:
+            if time.monotonic() > t_abort:
+                # host-side wall-clock abort: a K < N window can never hold a GPU lease hostage (round 1, call 36)
+                print("bench: K<N window aborted after the wall-clock limit at global step %d (target %d)" % (known, target),
+                      file=sys.stderr)
+                backend.debug_dump(sys.stderr)
+                os._exit(3)
             if careful or since >= 8 or known + since >= target - 16:
                 now = backend.device_epoch                   # synchronises this replica's stream
                 if now - known > since:
@@ -252,14 +260,20 @@ def main():
         return int(accepted.item()) * B
 
     # ---- warm-up (captures the graphs) ------------------------------------------------------------------------
-    for i in range(max(args.warmup, 3)):
+    # at least 30 untimed steps: the first two capture the step graphs, the next ones bring the host-side launch path, the
+    # copy engine and the L2-resident working set (weights, activations) to steady state; the count is reported as `warmup`
+    n_warm = max(args.warmup, 30)
+    for i in range(n_warm):
         device_step(i)
     barrier()
 
     # ---- device-timed K steps ------------------------------------------------------------------------------------
+    # (NVML queries take a driver lock that kernel launches also need: one sampling thread per BOX, on rank 0's GPU -- eight of
+    #  them polling every 4 ms showed up as launch jitter, i.e. as arrival skew in the aggregation kernel)
     sampler = ClockSampler(ctx.device.index or 0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     barrier()
     e0.record()
     if k == n:
@@ -318,12 +332,16 @@ def main():
     if args.trace:
         write_timeline(args.trace, device_step, barrier, rank)
 
+    # per-rank %globaltimer phases of the LAST step's aggregation kernels: who waited for whom (the rank with the shortest
+    # arrival wait is the one everybody else waited for)
+    my_ph = {"late": backend.read_phases(), "early": backend.read_phases_early() if getattr(engine, "_bucketed", False) else None}
+    all_ph = backend.all_gather_object(my_ph)
     if rank == 0:
         value = images_dev / (ms_total / 1e3)
         e2e_value = images_e2e / (ms2_total / 1e3)
         out = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": n, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "warmup": n_warm, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "impl": "ours",
             "config": {"model": ("LeNet-like MNIST convnet (1,663,370 params, reference src/mnist.py)" if args.model == "lenet"
@@ -346,8 +364,15 @@ def main():
             "gpu_launches": launches, "gpu_launches_per_step": engine.launches_per_step,
             "final_global_step": info.global_step,
             "sync_phases_ns": dict(zip(["start", "decided", "reduced", "pushed", "landed", "end"], backend.read_phases())),
-            "sync_early_phases_ns": (dict(zip(["start", "arrived", "cta0_done", "all_pushed"], backend.read_phases_early()))
+            "sync_early_phases_ns": (dict(zip(["start", "arrived", "reduced_cta0", "all_pushed", "all_landed", "applied_cta0"],
+                                              backend.read_phases_early()))
                                      if getattr(engine, "_bucketed", False) else None),
+            "sync_phases_all_ranks_ns": [p["late"] for p in all_ph],
+            "sync_early_phases_all_ranks_ns": [p["early"] for p in all_ph],
+            "aggregation": ("bucketed v2: bf16-wire fc1 bucket under the backward pass + pushed late bucket (csrc/fused_bucket.cu)"
+                            if getattr(engine, "_bucket_v2", False) else
+                            ("bucketed v1 (fp32 two-shot early + one-shot late)" if getattr(engine, "_bucketed", False)
+                             else "single fused kernel")),
         }
         print(json.dumps(out))
     sys.stdout.flush()

@@ -91,7 +91,7 @@ DMNIST_DEVICE void load_patch_half(PatchRegs& pr, int h, long long P, long long 
   }
 }
 
-DMNIST_DEVICE void store_im2col_half(uint8_t* a_tiles, int m, int h, const PatchRegs& pr) {
+DMNIST_DEVICE void store_im2col_half(uint8_t* a_tiles, int m, int h, const PatchRegs& pr, int tile_bytes = C1T_AP_BYTES) {
 #pragma unroll
   for (int px = 0; px < 2; ++px) {
     uint32_t w[16];                                   // 32 taps as bf16 pairs
@@ -102,7 +102,7 @@ DMNIST_DEVICE void store_im2col_half(uint8_t* a_tiles, int m, int h, const Patch
       const float v1 = t1 < 25 ? pr.v[t1 / 5][px + t1 % 5] : (t1 == 25 ? pr.one : 0.f);
       w[j] = pack_bf16x2(v0, v1);
     }
-    uint8_t* tile = a_tiles + (2 * h + px) * C1T_AP_BYTES;
+    uint8_t* tile = a_tiles + (2 * h + px) * tile_bytes;
 #pragma unroll
     for (int c = 0; c < 4; ++c) sts128(tile + swz64(m, c), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
   }
@@ -402,6 +402,147 @@ conv1_wgrad_tc_kernel(const float* __restrict__ images,          // [B,28,28]
   if (warp == 0) tmem_dealloc<32>(tmem_base);
 }
 
+struct C1Wg64Smem {
+  static constexpr int TILE_BYTES = 64 * 64;                     // 64 pooled pixels x 32 bf16
+  static constexpr int STAGE_BYTES = 8 * TILE_BYTES;            // A_0..A_3 then G_0..G_3 (32 KB)
+  static constexpr int BAR_OFF = 2 * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 128 + 1024;
+};
+
+// 64-pixel-tile variant (round-2 candidate, DMNIST_C1WG_TILE=64): 2 x 32 KB of shared memory instead of 2 x 64 KB, so a CTA
+// fits next to conv2_wgrad's (135 KB) and the two weight-gradient kernels at the end of the step can overlap instead of
+// running back to back.  Warp 0: MMA issuer, warps 1-4: builders (two per pooled pixel), warp 4 also the epilogue.
+__global__ void __maxnreg__(128)
+conv1_wgrad_tc64_kernel(const float* __restrict__ images,          // [B,28,28]
+                      const __nv_bfloat16* __restrict__ dpool,   // [B,14,14,32] gradient w.r.t. the pooled activations
+                      const uint8_t* __restrict__ code,          // [B,14,14,32]
+                      float* __restrict__ g_w,                   // [25][32], accumulated atomically (pre-zeroed)
+                      float* __restrict__ g_b,                   // [32]
+                      long long total, int num_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + C1Wg64Smem::BAR_OFF);   // [2] 128 arrivals
+  uint64_t* empty = full + 2;                                              // [2] 1 arrival (tcgen05.commit)
+  uint64_t* acc_full = empty + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(acc_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // contiguous tile range per CTA
+  const int t_begin = (int)(((long long)num_tiles * blockIdx.x) / gridDim.x);
+  const int t_end = (int)(((long long)num_tiles * (blockIdx.x + 1)) / gridDim.x);
+  const int nt = t_end - t_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<32>(tmem_holder);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();
+
+  if (warp == 0) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, 32, /*A MN*/ true, /*B MN*/ true);
+    for (int i = 0; i < nt; ++i) {
+      const int s = i & 1;
+      mbar_wait_wd(&full[s], (i >> 1) & 1);
+      tc_fence_after_sync();
+      if (elect_one()) {
+        const uint32_t base = smem_u32(smem + s * C1Wg64Smem::STAGE_BYTES);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          // A_p (MN-major): k-row = pooled pixel (64 B), 8-row groups 512 B apart; M = 128 needs four 32-tap chunks, only
+          //   the first is real: the other three (LBO = 8 KB = the following tiles) land in accumulator rows 32-127,
+          //   which nobody reads.  G_p (MN-major): k-row = pooled pixel, N = 32 channels = one chunk.
+          const uint64_t da0 = make_smem_desc(base + p * C1Wg64Smem::TILE_BYTES, C1Wg64Smem::TILE_BYTES, 512, SWZ_64B);
+          const uint64_t db0 = make_smem_desc(base + (4 + p) * C1Wg64Smem::TILE_BYTES, C1Wg64Smem::TILE_BYTES, 512, SWZ_64B);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)     // K = 64 pixels = 4 x UMMA_K; 16 k-rows = 1024 B
+            umma_bf16(tmem_base, da0 + (uint64_t)((1024 * k) >> 4), db0 + (uint64_t)((1024 * k) >> 4), idesc, (i | p | k) != 0);
+        }
+        umma_commit(&empty[s]);
+        if (i == nt - 1) umma_commit(acc_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int h = (warp - 1) >> 1, m = ((warp - 1) & 1) * 32 + lane;   // two builders per pooled pixel: window rows h = 0, 1
+    struct TileRegs {
+      PatchRegs patch;
+      uint4 gq[4];      // pooled gradient, 32 channels bf16
+      uint4 cq[2];      // pooling codes, 32 channels
+    };
+    auto load_tile = [&](TileRegs& tr, int i) {
+      const long long P = (long long)(t_begin + i) * 64 + m;
+      load_patch_half(tr.patch, h, P, total, images);
+      if (P < total) {
+        const uint4* gp = reinterpret_cast<const uint4*>(dpool + (size_t)P * 32);
+        const uint4* cp = reinterpret_cast<const uint4*>(code + (size_t)P * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tr.gq[j] = gp[j];
+        tr.cq[0] = __ldg(cp);
+        tr.cq[1] = __ldg(cp + 1);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tr.gq[j] = make_uint4(0, 0, 0, 0);
+        tr.cq[0] = tr.cq[1] = make_uint4(0, 0, 0, 0);
+      }
+    };
+    TileRegs cur, nxt;
+    if (nt > 0) load_tile(cur, 0);
+    for (int i = 0; i < nt; ++i) {
+      const int s = i & 1;
+      uint8_t* stage = smem + s * C1Wg64Smem::STAGE_BYTES;
+      if (i + 1 < nt) load_tile(nxt, i + 1);        // next tile's global loads are in flight while this one is packed
+      mbar_wait_wd(&empty[s], ((i >> 1) & 1) ^ 1);
+      store_im2col_half(stage, m, h, cur.patch, C1Wg64Smem::TILE_BYTES);
+      const uint4* gq = cur.gq;
+      const uint4* cq = cur.cq;
+      const uint32_t g32[16] = {gq[0].x, gq[0].y, gq[0].z, gq[0].w, gq[1].x, gq[1].y, gq[1].z, gq[1].w,
+                                gq[2].x, gq[2].y, gq[2].z, gq[2].w, gq[3].x, gq[3].y, gq[3].z, gq[3].w};
+      const uint32_t cw[8] = {cq[0].x, cq[0].y, cq[0].z, cq[0].w, cq[1].x, cq[1].y, cq[1].z, cq[1].w};
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        const uint32_t p = 2u * (uint32_t)h + (uint32_t)px;
+        uint32_t o[16];
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) {     // same byte-parallel mask as the unpool epilogue of gemm_tc.cu
+          const uint32_t xz = (cw[w8] & 0x07070707u) ^ (0x04040404u | (0x01010101u * p));
+          const uint32_t hit = ~(xz + 0x7f7f7f7fu) & 0x80808080u;
+          o[2 * w8] = g32[2 * w8] & prmt(hit, 0u, 0x9988u);
+          o[2 * w8 + 1] = g32[2 * w8 + 1] & prmt(hit, 0u, 0xbbaau);
+        }
+        uint8_t* tile = stage + (4 + p) * C1Wg64Smem::TILE_BYTES;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sts128(tile + swz64(m, c), o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&full[s]);
+      cur = nxt;
+    }
+    if (nt > 0 && warp == 4) {
+      // accumulator rows 0-31 = taps (25 = bias); this warp owns TMEM lanes 0-31
+      mbar_wait_wd(acc_full, 0);
+      tc_fence_after_sync();
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base, v);
+      tmem_ld_wait();
+      if (lane < 26) {
+        float* o = lane < 25 ? g_w + lane * 32 : g_b;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          red_add_f32x4(o + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                        __uint_as_float(v[j + 3]));
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<32>(tmem_base);
+}
+
 }  // namespace dm
 
 extern "C" {
@@ -438,6 +579,21 @@ int dm_conv1_wgrad_tc(const void* images, const void* dpool, const void* code, v
     configured = true;
   }
   const long long total = (long long)B * 196;
+  static const int tile = env_int("DMNIST_C1WG_TILE", 64);
+  if (tile == 64) {
+    static bool configured64 = false;
+    if (!configured64) {
+      DM_CUDA_OK(cudaFuncSetAttribute(conv1_wgrad_tc64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C1Wg64Smem::TOTAL));
+      DM_CUDA_OK(cudaFuncSetAttribute(conv1_wgrad_tc64_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      configured64 = true;
+    }
+    const int tiles64 = (int)((total + 63) / 64);
+    const int grid64 = tiles64 < g_max_ctas ? tiles64 : g_max_ctas;
+    return (int)launch_kernel(conv1_wgrad_tc64_kernel, dim3(grid64), dim3(160), C1Wg64Smem::TOTAL,
+                              reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const float*>(images),
+                              reinterpret_cast<const __nv_bfloat16*>(dpool), reinterpret_cast<const uint8_t*>(code),
+                              reinterpret_cast<float*>(g_w), reinterpret_cast<float*>(g_b), total, tiles64);
+  }
   const int tiles = (int)((total + C1T_TILE - 1) / C1T_TILE);
   const int grid = tiles < g_max_ctas ? tiles : g_max_ctas;
   return (int)launch_kernel(conv1_wgrad_tc_kernel, dim3(grid), dim3(C1T_WG_THREADS), C1WgSmem::TOTAL,

@@ -77,7 +77,11 @@ __global__ void __launch_bounds__(EARLY2_THREADS) bucket_early_kernel(SyncPeers 
   const int stride = gridDim.x * EARLY2_THREADS;
   const int tid = blockIdx.x * EARLY2_THREADS + threadIdx.x;
   __nv_bfloat16* mine = r.g16[a.rank];
-  if (blockIdx.x == 0 && threadIdx.x == 0) me->t_phase_e[0] = globaltimer_ns();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const unsigned long long now = globaltimer_ns();
+    me->t_phase_e[0] = now;
+    if (NR == 1) { me->t_phase_e[1] = now; me->t_phase_e[2] = now; me->t_phase_e[3] = now; me->t_phase_e[4] = now; }
+  }
 
   if (NR > 1) {
     // ---- every rank's fc1_wgrad is complete (all-to-all flags: CTA 0 tells the peers, everybody watches the local words) ----
@@ -213,6 +217,9 @@ __global__ void __launch_bounds__(LATE2_THREADS, 1) bucket_late_kernel(SyncPeers
     const unsigned long long now = globaltimer_ns();
     me->t_arrive[epoch % TIMING_RING] = now;     // "gradient complete" stamp: compute time excludes the barrier below
     me->t_phase[0] = now;
+    if (NR == 1) me->t_phase[1] = now;
+    // K == N: the step's outcome is known before it starts -- tell the host now, the PCIe trip overlaps the exchange
+    publish_status(me, epoch + 1, me->accepted_steps + 1, me->dropped_steps, (NR >= 32) ? 0xffffffffu : ((1u << NR) - 1u), (uint32_t)NR, 0u);
   }
   const size_t half = (size_t)(epoch & 1u) * (size_t)NR * (size_t)n_late4;   // inbox half of this step (float4 units)
 

@@ -137,6 +137,8 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_sgd_kernel(SyncPee
   __syncthreads();
   const uint32_t mask = s_mask, late = s_late;
   const int count = __popc(mask);
+  if (blockIdx.x == 0 && threadIdx.x == 0)     // the step's outcome is decided: tell the host now, the PCIe trip overlaps the reduction
+    publish_status(me, s_target, me->accepted_steps + (late ? 0u : 1u), me->dropped_steps + (late ? 1u : 0u), mask, (uint32_t)count, late);
   int own_begin = 0, own_end = 0;   // float4 range whose shadow this rank writes in the update loop
 
   if (!late && count > 0) {
@@ -414,6 +416,7 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_late_kernel(SyncPe
     const unsigned long long now = globaltimer_ns();
     me->t_arrive[epoch % TIMING_RING] = now;
     me->t_phase[0] = now;
+    publish_status(me, epoch + 1, me->accepted_steps + 1, me->dropped_steps, (1u << a.nranks) - 1u, (uint32_t)a.nranks, 0u);
   }
   if (threadIdx.x < a.nranks) {
     if (blockIdx.x == 0) st_release_sys(&P.ctrl[threadIdx.x]->arrive[a.rank * 32], epoch + 1);
@@ -538,6 +541,7 @@ int dm_sync_ctrl_offset(const char* field) {
   DM_OFF(cta_counter); DM_OFF(t_phase); DM_OFF(t_phase_e); DM_OFF(arrive); DM_OFF(done); DM_OFF(arrive_e); DM_OFF(done_e);
   DM_OFF(commit_local); DM_OFF(bitmap); DM_OFF(commit); DM_OFF(last_in_mask); DM_OFF(decided_tag); DM_OFF(decided_mask);
   DM_OFF(decided_late); DM_OFF(decided_target); DM_OFF(cta_counter_e); DM_OFF(cta_counter2);
+  DM_OFF(status_seq); DM_OFF(host_mirror); DM_OFF(iv_state); DM_OFF(iv_busy); DM_OFF(iv_deadline); DM_OFF(iv_ticks_committed);
 #undef DM_OFF
   return -1;
 }
@@ -622,6 +626,14 @@ int dm_fused_sync_bucket(void* const* ctrl, void* const* params, void* const* gr
     return -5;     // bucketed path is instantiated for 2, 4 and 8 replicas; the caller falls back to the single kernel
   }
   return (int)launch_kernel(fused_sync_late_kernel, dim3(ctas), dim3(SYNC_THREADS), 0, stream, P, a, r);
+}
+
+// Point the control block's host mirror at `host_ptr` (page-locked, device-accessible host memory: 4 slots x 8 words) or null.
+int dm_sync_set_host_mirror(void* ctrl, void* host_ptr) {
+  using dm::SyncCtrl;
+  DM_CUDA_OK(cudaMemcpy(reinterpret_cast<char*>(ctrl) + offsetof(SyncCtrl, host_mirror), &host_ptr, sizeof(void*),
+                        cudaMemcpyHostToDevice));
+  return 0;
 }
 
 int dm_f32_to_bf16(const void* src, void* dst, long long numel, void* stream_) {

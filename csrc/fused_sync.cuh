@@ -50,6 +50,25 @@ struct SyncCtrl {
   uint32_t cta_counter2;         // late bucket kernel: CTAs that have finished (the last one closes the step)
   uint32_t pad2[30];
   unsigned long long t_phase_e[8];            // early kernel: start, arrived, reduced (CTA 0), all pushed, all landed, applied (CTA 0)
+  // ---- device-side interval mode (mode C, csrc/fused_interval.cu) ------------------------------------------------------------
+  volatile unsigned long long iv_state;    // ((step+1) << 32) | gradients accumulated for that step -- read by the committer
+  volatile uint32_t iv_busy;               // step+1 while an accumulate for that step is in flight (Dekker pair of commit_local)
+  volatile uint32_t iv_last_total;         // written by the committer: divisor of the tick that produced my current weights
+  unsigned long long iv_deadline;          // local %globaltimer deadline of the current tick
+  unsigned long long iv_interval_ns;
+  uint32_t iv_adopted;                     // this iteration adopted new weights: refresh the bf16 shadow
+  uint32_t iv_go;                          // this iteration's gradient may be accumulated (its step is still open)
+  uint32_t iv_commit_go;                   // step+1: I won the commit of that step -> the apply kernel reduces + pushes
+  uint32_t iv_commit_mask;                 // contributors of the tick I am committing
+  uint32_t iv_commit_total;                // its divisor (sum of the contributors' counts)
+  uint32_t iv_ticks_committed;             // ticks this rank committed (statistics)
+  uint32_t cta_counter_iv;
+  // ---- host mirror of the status words: the kernel that closes a step writes (epoch, error, accepted, dropped, last_mask,
+  // last_count, last_late, seq) into page-locked HOST memory (zero-copy store over PCIe) so the training loop learns a step's
+  // outcome without a device read or a memcpy node in the step graph (a D2H memcpy node costs the graph ~10 us) ------------------
+  uint32_t status_seq;                     // number of steps closed so far (ring index of the mirror slot = seq & 3)
+  uint32_t* host_mirror;                   // 4 slots x 8 words in mapped pinned host memory, or null
+  uint32_t pad3[16];
 };
 
 struct SyncPeers {
@@ -118,6 +137,22 @@ DMNIST_DEVICE void multimem_st_f4(float* mc, float4 v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z),
                "f"(v.w)
                : "memory");
+}
+
+// Host mirror of a step's outcome.  Called by ONE thread per step, as EARLY as the outcome is known (the values are passed
+// in, the control-block words themselves are updated when the step closes): the stores travel to page-locked host memory over
+// PCIe while the kernel does its work, and are complete when the kernel -- hence the step's completion event -- is.  No fence:
+// the host only reads the slot after waiting for that event, and checks the seq word against the step it expects.
+DMNIST_DEVICE void publish_status(SyncCtrl* me, uint32_t epoch_after, uint32_t accepted, uint32_t dropped, uint32_t mask,
+                                  uint32_t count, uint32_t late) {
+  const uint32_t seq = me->status_seq;
+  uint32_t* m = me->host_mirror;
+  if (m != nullptr) {
+    m += 8 * (seq & 3u);
+    *reinterpret_cast<uint4*>(m) = make_uint4(epoch_after, me->error, accepted, dropped);
+    *reinterpret_cast<uint4*>(m + 4) = make_uint4(mask, count, late, seq + 1);
+  }
+  me->status_seq = seq + 1;
 }
 
 DMNIST_DEVICE float device_lr(const SyncArgs& a, uint32_t step) {

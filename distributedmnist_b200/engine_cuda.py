@@ -40,6 +40,21 @@ from .parallel.backends import StepInfo
 from .parallel.fused import FusedBackend
 
 
+class _RunnerEvent:
+    """Completion of a step launched through the native runner: ``synchronize()`` like a ``torch.cuda.Event``."""
+
+    def __init__(self, lib, runner, slot: int):
+        self.lib, self.runner, self.slot = lib, runner, slot
+
+    def synchronize(self) -> None:
+        rc = self.lib.dm_runner_wait(self.runner, self.slot)
+        if rc != 0:
+            raise RuntimeError("dm_runner_wait failed: CUDA error %d" % rc)
+
+    def query(self) -> bool:
+        return self.lib.dm_runner_query(self.runner, self.slot) == 1
+
+
 class CudaLeNetEngine(ComputeEngine):
     def __init__(self, batch_size: int, backend: FusedBackend, seed: int = 66478, rank: int = 0,
                  keep_prob: float = 0.5, use_graph: bool = True):
@@ -109,12 +124,22 @@ class CudaLeNetEngine(ComputeEngine):
         self._bucket_split = p_fc1.offset
         self._bucket_early = (p_fc1.offset, p_fc1.offset + p_fc1.numel)
         self._bucketed = False
+        self._bucket_v2 = False       # bf16-wire early bucket + pushed late bucket (csrc/fused_bucket.cu)
+        self._g16 = self._g16_view = self._inbox = None
         self._epoch_ptr = ctypes.c_void_p(backend.ctrl.local_ptr + backend._off["epoch"])
         self.launches_per_step = 0
 
     # ---- inputs ------------------------------------------------------------------------------
+    def _leave_native_runner(self) -> None:
+        """The torch-dispatched path takes over again: its events know nothing about steps the native runner launched."""
+        if getattr(self, "_runner", None) is not None:
+            torch.cuda.synchronize()
+            self.lib.dm_runner_destroy(self._runner)
+            self._runner = None
+
     def load_batch(self, images, labels) -> None:
         """Pinned host staging -> device slot, on the copy stream (overlaps the previous step)."""
+        self._leave_native_runner()
         s = self._loaded & 1
         if isinstance(images, torch.Tensor) and images.dtype == torch.float32 and labels.dtype == torch.int64 \
                 and ((images.is_pinned() and labels.is_pinned()) or (images.is_cuda and labels.is_cuda)):
@@ -153,6 +178,7 @@ class CudaLeNetEngine(ComputeEngine):
     def load_packed(self, packed: torch.Tensor) -> None:
         """Packed batch (see :meth:`pack_batch`; pinned host or device memory) -> device slot with one copy on the copy
         stream.  The buffer must stay untouched until the step after the next one has been enqueued."""
+        self._leave_native_runner()
         s = self._loaded & 1
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self._slot_free[s])
@@ -163,6 +189,44 @@ class CudaLeNetEngine(ComputeEngine):
 
     def h2d_bytes_per_step(self) -> int:
         return self._h2d_bytes
+
+    # ---- native step executor (csrc/step_runner.cu) ----------------------------------------------------------------------
+    def step_packed(self, packed: torch.Tensor):
+        """One whole training step from a packed batch (see :meth:`pack_batch`; pinned host or device memory): input DMA,
+        event chaining and the graph launch happen in ONE native call once both slot graphs exist (``DMNIST_NATIVE_RUNNER=0``
+        keeps the torch-dispatched path).  Returns ``(waitable, loss buffer, seq)`` like :meth:`read_result_async`."""
+        r = getattr(self, "_runner", None)
+        if r is None and self.use_graph and self._opt_args is not None and os.environ.get("DMNIST_NATIVE_RUNNER", "1") != "0" \
+                and all(g is not None and g[1] for g in self._graphs):
+            r = self._make_runner()
+        if r is None:
+            self.load_packed(packed)
+            self.train_step()
+            return self.read_result_async()
+        s = int(self.lib.dm_runner_step(r, ctypes.c_void_p(packed.data_ptr())))
+        if s < 0:
+            raise RuntimeError("dm_runner_step failed: CUDA error %d" % -s)
+        self._keep_alive[s] = packed                     # the DMA reads it asynchronously
+        self._slot = s
+        self._loaded += 1
+        self._steps_launched += 1
+        return _RunnerEvent(self.lib, r, s), self.h_loss_bufs[s], self._seq0 + self._steps_launched
+
+    def _make_runner(self):
+        torch.cuda.synchronize()                         # hand-over point: nothing of the torch-dispatched path is in flight
+        lib = self.lib
+        lib.dm_runner_create.restype = ctypes.c_void_p
+        cur = torch.cuda.current_stream()
+        r = lib.dm_runner_create(ctypes.c_void_p(cur.cuda_stream), ctypes.c_void_p(self.copy_stream.cuda_stream),
+                                 ctypes.c_void_p(self._graphs[0][0].raw_cuda_graph_exec()),
+                                 ctypes.c_void_p(self._graphs[1][0].raw_cuda_graph_exec()),
+                                 ctypes.c_void_p(self.in_dev[0].data_ptr()), ctypes.c_void_p(self.in_dev[1].data_ptr()),
+                                 ctypes.c_ulonglong(self._in_bytes), int(self._loaded & 1))
+        if not r:
+            return None
+        self._runner = ctypes.c_void_p(r)
+        self._keep_alive = [None, None]
+        return self._runner
 
     # ---- optimizer binding ------------------------------------------------------------------------
     def attach_optimizer(self, opt) -> None:
@@ -176,12 +240,35 @@ class CudaLeNetEngine(ComputeEngine):
         self._straggler = getattr(opt, "_straggler", None)
         self._stamp = getattr(opt, "mode", "") == "cdf"
         self._graphs = [None, None]
+        self._runner = None                  # graphs are re-captured: the native runner is rebuilt on demand
+        # mode C on the device (csrc/fused_interval.cu): every iteration adds its gradient to a symmetric accumulator; ticks
+        # are committed by whichever replica first passes the %globaltimer deadline
+        self._interval = getattr(opt, "mode", "") == "interval"
+        if self._interval and getattr(self, "_acc", None) is None:
+            self._acc = self.backend.allocate(self.spec.arena_numel)
         # Bucketed aggregation (csrc/fused_sync.cu): full participation on 2/4/8 replicas.  fc1's weight gradient (96.5 % of
         # the bytes) is exchanged by small co-resident CTAs NEXT TO conv2 dgrad/wgrad + conv1 wgrad; the rest goes one-shot.
+        #   DMNIST_BUCKET=2 (default): csrc/fused_bucket.cu -- fc1's gradient leaves the GEMM epilogue as bf16, is reduced in
+        #     place over NVLink (in-switch fp32 accumulation) and applied to the local fp32 master weights under the backward
+        #     pass; the small bucket is pushed into every replica's inbox.  Also used on ONE replica (no exchange, the fc1
+        #     update still leaves the critical path).   =1: round-1 fp32 two-shot / one-shot kernels.   =0: single kernel.
         n = self.backend.ctx.world_size
-        self._bucketed = (hasattr(self, "_bucket_split") and n in (2, 4, 8) and int(k) == n and self._branches
-                          and self.backend.drop_keep <= 0.0 and os.environ.get("DMNIST_BUCKET", "1") != "0")
+        mode = os.environ.get("DMNIST_BUCKET", "2")
+        can = (hasattr(self, "_bucket_split") and int(k) == n and self._branches and self.backend.drop_keep <= 0.0
+               and getattr(opt, "mode", "") != "interval")
+        self._bucket_v2 = can and mode == "2" and n in (1, 2, 4, 8)
+        self._bucketed = can and ((mode == "1" and n in (2, 4, 8)) or self._bucket_v2)
+        if self._bucket_v2 and self._g16 is None:
+            e0, e1 = self._bucket_early
+            assert e0 % 8 == 0 and (e1 - e0) % 8 == 0, "fc1 weights must start on a 32-byte boundary of the arena"
+            self._g16 = self.backend.allocate_buffer((e1 - e0) * 2)
+            self._g16_view = self._g16.view(torch.bfloat16, 0, e1 - e0).view(3136, 512)
+            n_late = self.spec.arena_numel - (e1 - e0)
+            self._inbox = self.backend.allocate_buffer(2 * n * n_late * 4) if n > 1 else None
         self._early_ctas = int(os.environ.get("DMNIST_EARLY_CTAS", "148"))
+        torch.cuda.synchronize()
+        self._seq0 = self.backend.status_seq       # steps closed on this control block before the engine's first one
+        self._steps_launched = 0
         self.lib.dm_set_max_ctas(int(os.environ.get("DMNIST_MAX_CTAS", "148")))
 
     def params_updated(self) -> None:
@@ -247,8 +334,13 @@ class CudaLeNetEngine(ComputeEngine):
         #  the SMs -- the data-gradient GEMM must be that one)
         with torch.cuda.stream(self._side[0] if branch else main):
             # fc1 wgrad: dW1[3136,512] = a2^T (A MN-major) * dh (B MN-major), K = batch; straight into the arena
-            G.gemm_bf16_raw(self.a2, self.dh, g["fc1_weights"], 3136, 512, B, 3136, 512, 512, True, True,
-                            G.EPI_STORE_F32, bn=128)
+            if early_sync and self._bucket_v2:
+                # ... as bf16 into the symmetric wire buffer: half the epilogue stores, half the NVLink bytes
+                G.gemm_bf16_raw(self.a2, self.dh, self._g16_view, 3136, 512, B, 3136, 512, 512, True, True,
+                                G.EPI_STORE_BF16, bn=128)
+            else:
+                G.gemm_bf16_raw(self.a2, self.dh, g["fc1_weights"], 3136, 512, B, 3136, 512, 512, True, True,
+                                G.EPI_STORE_F32, bn=128)
             if not early_sync:
                 # fc2 weight/bias + fc1 bias gradients: only the aggregation kernel consumes them
                 check(lib.dm_fc2_wgrad(ptr(self.h_act), ptr(self.dlogits), ptr(self.dh), ptr(g["fc2_weights"]),
@@ -267,8 +359,13 @@ class CudaLeNetEngine(ComputeEngine):
                     self.backend.enqueue_straggler_delay(self._straggler.prob, self._straggler.usec, stream=self._side[0])
                 oa = self._opt_args
                 e0, e1 = self._bucket_early
-                self.backend.enqueue_bucket(self.params, self.grads, 1, e0, e1, e0, e1, oa["lr0"], oa["decay_rate"],
-                                            oa["decay_steps"], ctas=self._early_ctas, stream=self._side[0])
+                if self._bucket_v2:
+                    self.backend.enqueue_bucket_v2(self.params, self.grads, self._g16, self._inbox, 1, e0, e1, oa["lr0"],
+                                                   oa["decay_rate"], oa["decay_steps"], ctas=self._early_ctas,
+                                                   stream=self._side[0])
+                else:
+                    self.backend.enqueue_bucket(self.params, self.grads, 1, e0, e1, e0, e1, oa["lr0"], oa["decay_rate"],
+                                                oa["decay_steps"], ctas=self._early_ctas, stream=self._side[0])
                 join1 = torch.cuda.Event()
                 join1.record(self._side[0])
             # the small fc gradients (fc2 weights/biases, fc1 biases) belong to the late bucket: their own branch
@@ -390,22 +487,35 @@ class CudaLeNetEngine(ComputeEngine):
         if self._stamp:
             self.backend.enqueue_stamp_start()
             n += 1
+        interval = with_sync and getattr(self, "_interval", False)
+        if interval:
+            self.backend.enqueue_interval_begin(self.params)
+            n += 2
         n += self._launch_zero()
         n += self._launch_forward(self.images[slot], self.labels[slot], self.batch_size, True)
-        bucketed = with_sync and self._bucketed
+        bucketed = with_sync and self._bucketed and not interval
         n += self._launch_backward(self.images[slot], self.batch_size, early_sync=bucketed)
         if bucketed:
             oa = self._opt_args
             e0, e1 = self._bucket_early
-            self.backend.enqueue_bucket(self.params, self.grads, 2, 0, self.spec.arena_numel, e0, e1,
-                                        oa["lr0"], oa["decay_rate"], oa["decay_steps"])
+            if self._bucket_v2:
+                self.backend.enqueue_bucket_v2(self.params, self.grads, self._g16, self._inbox, 2, e0, e1, oa["lr0"],
+                                               oa["decay_rate"], oa["decay_steps"])
+            else:
+                self.backend.enqueue_bucket(self.params, self.grads, 2, 0, self.spec.arena_numel, e0, e1,
+                                            oa["lr0"], oa["decay_rate"], oa["decay_steps"])
             n += 2 + (1 if self._straggler is not None else 0)
         elif with_sync:
             if self._straggler is not None:
                 self.backend.enqueue_straggler_delay(self._straggler.prob, self._straggler.usec)
                 n += 1
-            self.backend.enqueue(self.params, self.grads, **self._opt_args)
-            n += 1
+            if interval:
+                oa = self._opt_args
+                self.backend.enqueue_interval_end(self.params, self.grads, self._acc, oa["lr0"], oa["decay_rate"], oa["decay_steps"])
+                n += 4
+            else:
+                self.backend.enqueue(self.params, self.grads, **self._opt_args)
+                n += 1
         if self._branches:
             torch.cuda.current_stream().wait_event(self._join_loss)      # the loss read-back branch rejoins at the end of the step
         self.launches_per_step = n
@@ -428,6 +538,8 @@ class CudaLeNetEngine(ComputeEngine):
             self._graphs[key][0].replay()
         else:
             self._launch_step(s, with_sync)
+        if with_sync:
+            self._steps_launched = getattr(self, "_steps_launched", 0) + 1
         self._slot_free[s].record(cur)
 
     # ---- public step API ----------------------------------------------------------------------------------
@@ -447,15 +559,20 @@ class CudaLeNetEngine(ComputeEngine):
         self.h_loss_acc = self.h_loss_bufs[s]
         return self._slot_free[s], self.h_loss_bufs[s]
 
+    def read_result_async(self):
+        """``(event, loss buffer, seq)`` of the step enqueued last: wait on the event, then ``loss[0]``/``loss[1]`` are (loss,
+        accuracy) and ``backend.mirror_info(seq)`` is the step's StepInfo -- both were written into page-locked host memory
+        by the step's own kernels, so the host never issues a device read."""
+        s = self._slot
+        return self._slot_free[s], self.h_loss_bufs[s], self._seq0 + self._steps_launched
+
     def loss_acc(self) -> Tuple[float, float]:
         ev, buf = self.read_loss_async()
         ev.synchronize()
         return float(buf[0]), float(buf[1])
 
     def step_info(self) -> StepInfo:
-        info = self.backend.last_step_info()
-        self.backend.check_error()
-        return info
+        return self.backend.last_step_info(check=True)     # one packed device->host read
 
     # ---- inference ------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -535,6 +652,9 @@ class CudaMlpEngine(ComputeEngine):
 
     # shared plumbing with the convnet engine
     load_batch = CudaLeNetEngine.load_batch
+    _leave_native_runner = CudaLeNetEngine._leave_native_runner
+    step_packed = CudaLeNetEngine.step_packed
+    _make_runner = CudaLeNetEngine._make_runner
     pack_batch = CudaLeNetEngine.pack_batch
     load_packed = CudaLeNetEngine.load_packed
     attach_optimizer = CudaLeNetEngine.attach_optimizer
@@ -543,6 +663,7 @@ class CudaMlpEngine(ComputeEngine):
     forward_backward = CudaLeNetEngine.forward_backward
     train_step = CudaLeNetEngine.train_step
     read_loss_async = CudaLeNetEngine.read_loss_async
+    read_result_async = CudaLeNetEngine.read_result_async
     loss_acc = CudaLeNetEngine.loss_acc
     step_info = CudaLeNetEngine.step_info
     _stamp = False
@@ -601,15 +722,25 @@ class CudaMlpEngine(ComputeEngine):
 
     def _launch_step(self, slot: int, with_sync: bool) -> None:
         B = self.batch_size
-        n = self._launch_zero()
+        n = 0
+        interval = with_sync and getattr(self, "_interval", False)
+        if interval:
+            self.backend.enqueue_interval_begin(self.params)
+            n += 2
+        n += self._launch_zero()
         n += self._forward(self.images[slot], self.labels[slot], B, True)
         n += self._backward(B)
         if with_sync:
             if self._straggler is not None:
                 self.backend.enqueue_straggler_delay(self._straggler.prob, self._straggler.usec)
                 n += 1
-            self.backend.enqueue(self.params, self.grads, **self._opt_args)
-            n += 1
+            if interval:
+                oa = self._opt_args
+                self.backend.enqueue_interval_end(self.params, self.grads, self._acc, oa["lr0"], oa["decay_rate"], oa["decay_steps"])
+                n += 4
+            else:
+                self.backend.enqueue(self.params, self.grads, **self._opt_args)
+                n += 1
         self.h_loss_bufs[slot].copy_(self.d_loss_acc, non_blocking=True)     # result read-back is part of the step
         self.launches_per_step = n
 

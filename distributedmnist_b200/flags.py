@@ -247,6 +247,10 @@ def define_engine_flags(F: FlagValues = FLAGS) -> FlagValues:
     F.DEFINE_integer("sync_timeout_ms", 30000, "Watchdog for device-side arrival polling")
     F.DEFINE_boolean("use_cuda_graph", True, "Capture the training step in a CUDA graph")
     F.DEFINE_boolean("use_nvls", True, "Use NVLS multimem reductions when the multicast object binds")
+    F.DEFINE_boolean("debug_sync", False, "Dump the aggregation control block (arrival / done words, bitmap, commit ring) "
+                                          "when a device-side watchdog fires (reference: the optimizer's debug Print ops)")
+    F.DEFINE_boolean("pipeline_steps", True, "GPU path: enqueue step i+1 before reading step i's loss / status words "
+                                             "(page-locked result buffers, background batch packer)")
     F.DEFINE_integer("log_every", 1, "Log every n-th local iteration (1 = reference behaviour)")
     F.DEFINE_float("dropout_keep_prob", 0.5, "Keep probability of the fc1 dropout (reference mnist.py:139)")
     return F

@@ -240,6 +240,57 @@ def check_end_to_end(B: int = 64, seed: int = 5) -> List[Result]:
     return out
 
 
+def check_bucketed_step_matches_single_kernel(B: int = 64, steps: int = 6, seed: int = 31) -> List[Result]:
+    """One replica, whole graph-replayed training steps: bucketed aggregation (csrc/fused_bucket.cu: fc1 gradient as bf16,
+    applied by the early kernel under the backward pass; small bucket by the late kernel) vs the single fused kernel."""
+    import os
+    from ..parallel.aggregators import SyncReplicasOptimizer
+    from ..schedule import LearningRateSchedule
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    xs = torch.rand(steps, B, 28, 28, generator=g) - 0.5
+    ys = torch.randint(0, 10, (steps, B), generator=g)
+    runs = {}
+    old = os.environ.get("DMNIST_BUCKET")
+    try:
+        for mode in ("2", "0"):
+            os.environ["DMNIST_BUCKET"] = mode
+            eng, be = _engine(B, seed)
+            eng.use_graph = True
+            eng.attach_optimizer(SyncReplicasOptimizer(be, LearningRateSchedule(0.05, 2, 0.5), 1, 1))
+            losses = []
+            p_init = eng.params.clone()
+            for s in range(steps):
+                eng.load_batch(xs[s], ys[s])
+                eng.train_step()
+                losses.append(eng.loss_acc()[0])
+                if s == 0:
+                    torch.cuda.synchronize()
+                    p_first = eng.params.clone()
+            torch.cuda.synchronize()
+            be.check_error()
+            runs[mode] = (eng.params.clone(), eng.shadow.float().clone(), losses, eng.step_info().global_step,
+                          bool(eng._bucket_v2), p_first, p_init)
+    finally:
+        if old is None:
+            os.environ.pop("DMNIST_BUCKET", None)
+        else:
+            os.environ["DMNIST_BUCKET"] = old
+    (p2, s2, l2, st2, v2, f2, i2), (p0, _s0, l0, st0, v0, f0, i0) = runs["2"], runs["0"]
+    pmax = p0.abs().max().item()
+    # after ONE step both paths applied the same gradient to the same weights, except that fc1's gradient went through bf16:
+    # |difference| <= 2^-8 * |update| elementwise (+ fp32 atomics noise); later steps amplify it through ReLU / max-pool /
+    # dropout decisions, so the final comparison is loose
+    upd = (f0 - i0).abs()
+    first_excess = ((f2 - f0).abs() - (upd * 2.0 ** -8 + 1e-6 * pmax)).max().item()
+    return [("bucket_v2.enabled", 0.0 if (v2 and not v0) else 1.0, 0.5),
+            ("bucket_v2.steps", abs(st2 - steps) + abs(st0 - steps), 0.5),
+            ("bucket_v2.first_step_excess", max(first_excess, 0.0) / pmax, 1e-6),
+            ("bucket_v2.first_update(rel, info)", upd.max().item() / pmax, 1e9),
+            ("bucket_v2.params_vs_single(rel)", (p2 - p0).abs().max().item() / pmax, 0.05),
+            ("bucket_v2.shadow(rel)", (s2 - p2).abs().max().item() / pmax, 0.01),
+            ("bucket_v2.loss", max(abs(a - b) for a, b in zip(l2, l0)), 0.02)]
+
+
 def check_training_reduces_loss(B: int = 128, steps: int = 40) -> List[Result]:
     from ..data import make_synthetic_mnist
     from ..parallel.aggregators import SyncReplicasOptimizer
@@ -295,4 +346,4 @@ def check_mlp2_end_to_end() -> List[Result]:
 
 
 ALL_CHECKS = [check_conv1_fwd, check_conv1_fwd_tc, check_conv1_wgrad, check_conv1_wgrad_simt, check_conv2_fwd, check_conv2_dgrad, check_conv2_wgrad, check_fc2_loss, check_fc1_dgrad_unpool,
-              check_end_to_end, check_training_reduces_loss, check_mlp_end_to_end, check_mlp2_end_to_end]
+              check_end_to_end, check_bucketed_step_matches_single_kernel, check_training_reduces_loss, check_mlp_end_to_end, check_mlp2_end_to_end]

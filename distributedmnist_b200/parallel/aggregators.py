@@ -187,14 +187,22 @@ class TimeoutReplicasOptimizer(_AggregatorBase):
         self._acc.add_(grads)
         self._acc_count += 1
         info = StepInfo(self.local_step, False, 0, 0, applied=False)
-        while self._clock() >= self._deadline(self._tick):
+        if self._clock() >= self._deadline(self._tick):
+            # ONE tick per call (every replica joins tick t exactly once, in its first call after deadline t), and after a
+            # late tick the next deadline is the first one still in the future *on the chief's clock* (exchanged inside the
+            # tick) -- missed deadlines are skipped, never replayed, and no replica decides on its own to run another tick
+            # (reference: the chief's timer sleeps the interval after each take_grad, …modified.py:208-215).
             lr = self.lr_schedule(self.local_step)
             res = self.backend.interval_tick(params, self._acc, self._acc_count, lr, self._tick)
-            self._tick += 1
+            chief_now = getattr(self.backend, "last_chief_clock", None)
+            nxt = self._tick + 1
+            if chief_now is not None and self._t0 is not None:
+                nxt = max(nxt, int((chief_now - self._t0) / self.interval_s))
+            self._tick = nxt
             self._acc.zero_()
             self._acc_count = 0
             if res.applied:
                 info = res
-            self._account(res) if res.applied else None
+                self._account(res)
         self.last_info = info
         return info

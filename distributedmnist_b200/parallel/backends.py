@@ -144,8 +144,9 @@ class _CollectiveBackend(Backend):
         cnt = torch.tensor([float(count)], dtype=torch.float32, device=acc.device)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         total = int(cnt.item())
-        flags = self.all_gather_object(int(count > 0))
-        mask = sum(1 << i for i, f in enumerate(flags) if f)
+        flags = self.all_gather_object((int(count > 0), time.monotonic()))
+        self.last_chief_clock = flags[0][1]        # replicas of one box share CLOCK_MONOTONIC: the chief's "now" of this tick
+        mask = sum(1 << i for i, f in enumerate(flags) if f[0])
         if total == 0:
             return StepInfo(self._global_step, False, 0, 0, applied=False)
         dist.all_reduce(acc, op=dist.ReduceOp.SUM)
@@ -163,8 +164,9 @@ class NcclBackend(_CollectiveBackend):
     name = "nccl"
 
 
-def make_backend(ctx: ReplicaContext, choice: str = "auto") -> Backend:
-    """``auto``: fused on GPU, gloo on multi-process CPU, local otherwise."""
+def make_backend(ctx: ReplicaContext, choice: str = "auto", flags=None) -> Backend:
+    """``auto``: fused on GPU, gloo on multi-process CPU, local otherwise.  ``flags`` (optional): ``--sync_timeout_ms``,
+    ``--use_nvls`` and ``--debug_sync`` configure the fused backend."""
     if choice == "auto":
         if ctx.on_gpu:
             choice = "fused"
@@ -179,5 +181,10 @@ def make_backend(ctx: ReplicaContext, choice: str = "auto") -> Backend:
         return NcclBackend(ctx) if ctx.world_size > 1 else LocalBackend(ctx)
     if choice == "fused":
         from .fused import FusedBackend  # imports the sm_100a extension; fails loudly if missing
-        return FusedBackend(ctx)
+        kw = {}
+        if flags is not None:
+            kw = dict(timeout_ms=float(getattr(flags, "sync_timeout_ms", 30000)),
+                      use_nvls=None if getattr(flags, "use_nvls", True) else False,
+                      debug_sync=bool(getattr(flags, "debug_sync", False)))
+        return FusedBackend(ctx, **kw)
     raise ValueError("unknown backend %r" % choice)

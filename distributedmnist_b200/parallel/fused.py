@@ -31,8 +31,10 @@ from .symm_mem import SymmetricBuffer, allocate_symmetric
 
 class FusedBackend(Backend):
     name = "fused"
+    _STATUS = ("epoch", "error", "accepted_steps", "dropped_steps", "last_mask", "last_count", "last_late")
 
-    def __init__(self, ctx: ReplicaContext, ctas: int = 0, timeout_ms: float = 30000.0):
+    def __init__(self, ctx: ReplicaContext, ctas: int = 0, timeout_ms: float = 30000.0, use_nvls: Optional[bool] = None,
+                 debug_sync: bool = False):
         super().__init__(ctx)
         assert ctx.on_gpu, "FusedBackend needs a GPU"
         self.lib = load()
@@ -44,7 +46,8 @@ class FusedBackend(Backend):
         # NVLS (in-switch reduction + multicast store) for the arenas when the fabric offers it; DMNIST_NVLS=0 -> P2P only
         #   DMNIST_NVLS unset: allocate multicast-capable arenas, use multimem from 4 replicas up (at 2 the peer path is
         #   faster: measured 106 vs 115 us/step, profiles/bench_r1_call23_2gpu.txt); =1 always; =0 never (CUDA-IPC arenas)
-        nv = os.environ.get("DMNIST_NVLS", "")
+        #   (--use_nvls=false forces the P2P kernels and CUDA-IPC arenas, like DMNIST_NVLS=0)
+        nv = os.environ.get("DMNIST_NVLS", "") if use_nvls is None else ("1" if use_nvls else "0")
         self.want_nvls = nv != "0"
         self.use_nvls = nv == "1" or (nv == "" and ctx.world_size >= 4)
         self.timeout_ms = timeout_ms
@@ -55,7 +58,20 @@ class FusedBackend(Backend):
         self._ctrl_bytes = self.ctrl.view(torch.uint8)
         self._off = {f: int(self.lib.dm_sync_ctrl_offset(f.encode())) for f in
                      ("epoch", "error", "accepted_steps", "dropped_steps", "last_mask", "last_count", "last_late",
-                      "global_step", "t_arrive", "t_start", "cta_counter", "t_phase", "t_phase_e")}
+                      "global_step", "t_arrive", "t_start", "cta_counter", "t_phase", "t_phase_e", "arrive", "done",
+                      "arrive_e", "done_e", "commit_local", "bitmap", "commit", "last_in_mask", "decided_tag",
+                      "decided_mask", "decided_late", "decided_target", "cta_counter_e", "cta_counter2", "status_seq",
+                      "host_mirror", "iv_state", "iv_busy", "iv_deadline", "iv_ticks_committed")}
+        assert all(v >= 0 for v in self._off.values()), self._off
+        # the host-readable status words (epoch .. last_late) sit next to each other: ONE device->host copy per query
+        self._status_lo = min(self._off[f] for f in self._STATUS)
+        self._status_hi = max(self._off[f] for f in self._STATUS) + 4
+        self.debug_sync = debug_sync or os.environ.get("DMNIST_DEBUG_SYNC", "0") == "1"
+        # host mirror of the status words: the kernel that closes a step stores them into page-locked host memory itself
+        self._mirror = torch.zeros(4 * 8, dtype=torch.int32).pin_memory()
+        check(self.lib.dm_sync_set_host_mirror(ctypes.c_void_p(self.ctrl.local_ptr), ctypes.c_void_p(self._mirror.data_ptr())),
+              "dm_sync_set_host_mirror")
+        self._mirror_np = self._mirror.numpy().view("<u4")
         self.shadow: Optional[torch.Tensor] = None     # bf16 copy of the parameter arena
         self.drop_keep = 0.0
         self.drop_seed = 0
@@ -67,6 +83,13 @@ class FusedBackend(Backend):
         t = buf.view(torch.float32, 0, numel)
         self._by_ptr[t.data_ptr()] = buf
         return t
+
+    def allocate_buffer(self, nbytes: int):
+        """Raw symmetric allocation (peer-mapped, NVLS-multicast-mapped when available): the bf16 gradient buffer and the
+        late-bucket inbox of the bucketed aggregation.  Collective: every rank calls it in the same order."""
+        buf = allocate_symmetric(int(nbytes), self.ctx.rank, self.ctx.world_size, self.ctx.device, self.want_nvls)
+        self._buffers.append(buf)
+        return buf
 
     def attach_shadow(self, params: torch.Tensor) -> torch.Tensor:
         """Create the local bf16 shadow arena of ``params`` and fill it."""
@@ -99,11 +122,72 @@ class FusedBackend(Backend):
         torch.cuda.synchronize()
         self.barrier()
 
-    def check_error(self) -> None:
-        e = self._read_u32("error")
+    def read_status(self) -> Dict[str, int]:
+        """epoch / error / accepted / dropped / last_mask / last_count / last_late with ONE device->host copy (synchronises
+        the current stream)."""
+        raw = self._ctrl_bytes[self._status_lo:self._status_hi].cpu().numpy().view("<u4")
+        return {f: int(raw[(self._off[f] - self._status_lo) // 4]) for f in self._STATUS}
+
+    @property
+    def status_seq(self) -> int:
+        """Number of steps closed on the device so far (device read)."""
+        return self._read_u32("status_seq")
+
+    def mirror_info(self, seq: int, check: bool = False) -> StepInfo:
+        """StepInfo of the ``seq``-th closed step (1-based) from the host mirror -- valid once that step's completion event
+        has been waited for; no device read.  Falls back to a device read if the slot was already overwritten (the host
+        fell more than three steps behind) or the mirror is not in use."""
+        m = self._mirror_np[8 * ((seq - 1) & 3):8 * ((seq - 1) & 3) + 8]
+        if int(m[7]) != seq:
+            return self.last_step_info(check=check)
+        st = dict(zip(self._STATUS, (int(x) for x in m[:7])))
+        if check:
+            self.check_error(st)
+        late = st["last_late"]
+        return StepInfo(global_step=st["epoch"], accepted=not late, mask=st["last_mask"], count=st["last_count"],
+                        stale=bool(late))
+
+    def check_error(self, status: Optional[Dict[str, int]] = None) -> None:
+        e = (status or self.read_status())["error"]
         if e:
-            raise RuntimeError("fused sync watchdog fired on rank %d: %s timeout"
-                               % (self.ctx.rank, {1: "arrival", 2: "push-complete"}.get(e, str(e))))
+            if self.debug_sync:
+                import sys
+                self.debug_dump(sys.stderr)
+            raise RuntimeError("fused sync watchdog fired on rank %d: %s timeout (DMNIST_DEBUG_SYNC=1 / --debug_sync dumps "
+                               "the control block)" % (self.ctx.rank, {1: "arrival", 2: "push-complete"}.get(e, str(e))))
+
+    def debug_dump(self, out=None) -> str:
+        """The accumulator / token-queue state of the reference's debug Print ops (…modified.py:230-234,383-387), here: every
+        handshake word of this rank's control block -- which peers have arrived / finished for which step, the chief's
+        arrival bitmap and commit ring, the local decision.  Printed when a watchdog fires under ``--debug_sync``."""
+        n = self.ctx.world_size
+        raw = self._ctrl_bytes.cpu().numpy()
+        u32 = lambda off: int(raw[off:off + 4].view("<u4")[0])           # noqa: E731
+        u64 = lambda off: int(raw[off:off + 8].view("<u8")[0])           # noqa: E731
+        lines = ["[sync-debug rank %d/%d] epoch=%d error=%d accepted=%d dropped=%d last(mask=%#x count=%d late=%d) global_step=%d"
+                 % (self.ctx.rank, n, u32(self._off["epoch"]), u32(self._off["error"]), u32(self._off["accepted_steps"]),
+                    u32(self._off["dropped_steps"]), u32(self._off["last_mask"]), u32(self._off["last_count"]),
+                    u32(self._off["last_late"]), u32(self._off["global_step"]))]
+        for f in ("arrive", "done", "arrive_e", "done_e"):
+            lines.append("  %-9s per peer (value = step+1): %s" % (f, [u32(self._off[f] + 128 * q) for q in range(n)]))
+        lines.append("  decided: tag=%d mask=%#x late=%d target=%d   cta counters: %d / %d / %d"
+                     % (u32(self._off["decided_tag"]), u32(self._off["decided_mask"]), u32(self._off["decided_late"]),
+                        u32(self._off["decided_target"]), u32(self._off["cta_counter"]), u32(self._off["cta_counter_e"]),
+                        u32(self._off["cta_counter2"])))
+        ep = u32(self._off["epoch"])
+        slots = sorted({(ep + d) % 64 for d in (-2, -1, 0, 1)})
+        lines.append("  commit_local[slot]=(step+1, mask): %s"
+                     % {sl: (u64(self._off["commit_local"] + 8 * sl) >> 32, hex(u64(self._off["commit_local"] + 8 * sl) & 0xffffffff))
+                        for sl in slots})
+        if self.ctx.rank == 0:
+            lines.append("  chief bitmap[slot]: %s   commit[slot]: %s   last_in_mask: %s"
+                         % ({sl: hex(u32(self._off["bitmap"] + 4 * sl)) for sl in slots},
+                            {sl: (u64(self._off["commit"] + 8 * sl) >> 32, hex(u64(self._off["commit"] + 8 * sl) & 0xffffffff)) for sl in slots},
+                            [u32(self._off["last_in_mask"] + 4 * q) for q in range(n)]))
+        txt = "\n".join(lines)
+        if out is not None:
+            print(txt, file=out, flush=True)
+        return txt
 
     def read_phases(self):
         """%globaltimer stamps of the last launch: start, decided, reduced, pushed, landed, end (ns, relative)."""
@@ -111,8 +195,9 @@ class FusedBackend(Backend):
         return [x - t[0] for x in t]
 
     def read_phases_early(self):
-        """Early-bucket kernel of the last step: start, arrived, reduced+pushed (CTA 0), all pushes out (ns, relative)."""
-        t = self._ctrl_bytes[self._off["t_phase_e"]:self._off["t_phase_e"] + 32].view(torch.int64).cpu().tolist()
+        """Early-bucket kernel of the last step: start, arrived, reduced (CTA 0), all pushes out, all shards landed,
+        applied (CTA 0) (ns, relative)."""
+        t = self._ctrl_bytes[self._off["t_phase_e"]:self._off["t_phase_e"] + 48].view(torch.int64).cpu().tolist()
         return [x - t[0] for x in t]
 
     def read_timing(self, first_step: int, last_step: int):
@@ -152,6 +237,52 @@ class FusedBackend(Backend):
             *self._mc_ptrs(pb, gb))
         check(rc, "dm_fused_sync_bucket")
 
+    def enqueue_bucket_v2(self, params: torch.Tensor, grads: torch.Tensor, g16, inbox, phase: int, fc1_begin: int,
+                          fc1_end: int, lr0: float, decay_rate: float = 1.0, decay_steps: int = 1, ctas: int = 0,
+                          stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Bucketed aggregation, bf16 wire (csrc/fused_bucket.cu).  ``phase`` 1: reduce the bf16 fc1 gradient buffer ``g16``
+        in place over NVLink (NVLS or P2P) and apply SGD to the local fp32 fc1 weights -- a side branch of the step graph;
+        ``phase`` 2: push the small bucket into every replica's ``inbox``, sum in rank order, SGD, close the step."""
+        pb, gb = self._by_ptr[params.data_ptr()], self._by_ptr[grads.data_ptr()]
+        on = self.use_nvls and self.ctx.world_size > 1
+        mc_g16 = g16.multicast_ptr if on else 0
+        mc_inbox = inbox.multicast_ptr if (on and inbox is not None) else 0
+        rc = self.lib.dm_bucket_sync(
+            self.ctrl.ptr_table(), pb.ptr_table(), gb.ptr_table(), g16.ptr_table(),
+            inbox.ptr_table() if inbox is not None else None, self.ctx.rank, self.ctx.world_size, int(phase),
+            ctypes.c_longlong(fc1_begin), ctypes.c_longlong(fc1_end), ctypes.c_longlong(params.numel()),
+            ctypes.c_float(lr0), ctypes.c_float(decay_rate), int(decay_steps), ctypes.c_double(self.timeout_ms),
+            ctypes.c_void_p(0 if self.shadow is None else self.shadow.data_ptr()), int(ctas), stream_ptr(stream),
+            ctypes.c_void_p(mc_g16), ctypes.c_void_p(mc_inbox))
+        check(rc, "dm_bucket_sync(phase %d)" % phase)
+
+    # ---- device-side interval mode (mode C, csrc/fused_interval.cu) ----------------------------------------------------------
+    def interval_arm(self, interval_ms: float) -> None:
+        """Start the interval clock on this replica (reference ``start_interval_updates``): first tick due in ``interval_ms``."""
+        self.barrier()                       # replicas start their clocks together (each uses its own %globaltimer afterwards)
+        check(self.lib.dm_interval_arm(ctypes.c_void_p(self.ctrl.local_ptr), ctypes.c_double(interval_ms), stream_ptr()),
+              "dm_interval_arm")
+        torch.cuda.synchronize()
+        self.barrier()
+
+    def enqueue_interval_begin(self, params: torch.Tensor, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Start of an interval-mode iteration: adopt weights a committer has pushed (step counter, bf16 shadow)."""
+        check(self.lib.dm_interval_begin(ctypes.c_void_p(self.ctrl.local_ptr), ctypes.c_void_p(params.data_ptr()),
+                                         ctypes.c_void_p(0 if self.shadow is None else self.shadow.data_ptr()),
+                                         ctypes.c_longlong(params.numel()), stream_ptr(stream)), "dm_interval_begin")
+
+    def enqueue_interval_end(self, params: torch.Tensor, grads: torch.Tensor, acc: torch.Tensor, lr0: float,
+                             decay_rate: float = 1.0, decay_steps: int = 1,
+                             stream: Optional[torch.cuda.Stream] = None) -> None:
+        """End of an interval-mode iteration: accumulate the gradient locally; after the tick's deadline try to commit the
+        tick (mean of whatever every replica has accumulated) -- never blocks on another replica's progress."""
+        pb, gb, ab = self._by_ptr[params.data_ptr()], self._by_ptr[grads.data_ptr()], self._by_ptr[acc.data_ptr()]
+        mc = pb.multicast_ptr if (self.use_nvls and pb.multicast_ptr) else 0
+        check(self.lib.dm_interval_end(self.ctrl.ptr_table(), pb.ptr_table(), gb.ptr_table(), ab.ptr_table(), self.ctx.rank,
+                                       self.ctx.world_size, ctypes.c_longlong(params.numel()), ctypes.c_float(lr0),
+                                       ctypes.c_float(decay_rate), int(decay_steps), ctypes.c_double(self.timeout_ms),
+                                       int(self.ctas), stream_ptr(stream), ctypes.c_void_p(mc)), "dm_interval_end")
+
     @property
     def nvls_active(self) -> bool:
         return self.use_nvls and bool(self._buffers) and all(b.multicast_ptr for b in self._buffers[:2])
@@ -170,18 +301,19 @@ class FusedBackend(Backend):
         self.drop_keep = float(keep_prob)
         self.drop_seed = 0x2545F491
 
-    def last_step_info(self) -> StepInfo:
-        late = self._read_u32("last_late")
-        return StepInfo(global_step=self._read_u32("epoch"), accepted=not late, mask=self._read_u32("last_mask"),
-                        count=self._read_u32("last_count"), stale=bool(late))
+    def last_step_info(self, check: bool = False) -> StepInfo:
+        st = self.read_status()
+        if check:
+            self.check_error(st)
+        late = st["last_late"]
+        return StepInfo(global_step=st["epoch"], accepted=not late, mask=st["last_mask"], count=st["last_count"],
+                        stale=bool(late))
 
     def sync_step(self, params, grads, lr, local_step, k, delay_s: float = 0.0) -> StepInfo:
         if delay_s > 0:
             self.enqueue_straggler_delay(1.0, delay_s * 1e6)
         self.enqueue(params, grads, k, lr0=float(lr))
-        info = self.last_step_info()   # device -> host read (synchronises)
-        self.check_error()
-        return info
+        return self.last_step_info(check=True)   # one device -> host read (synchronises)
 
     def interval_tick(self, params, acc, count, lr, tick) -> StepInfo:
         """Mode C tick: every rank joins; ranks with an empty accumulator contribute zeros and the

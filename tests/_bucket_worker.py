@@ -45,7 +45,7 @@ def main():
                      "fp": fp(eng.params), "shadow_err": (eng.shadow.float() - eng.params).abs().max().item(),
                      "pmax": eng.params.abs().max().item(), "sample": eng.params[::40009].cpu().tolist()})
     be.check_error()
-    json.dump({"rank": r, "bucketed": bool(eng._bucketed), "nvls": bool(be.nvls_active), "rows": rows,
+    json.dump({"rank": r, "bucketed": bool(eng._bucketed), "v2": bool(eng._bucket_v2), "nvls": bool(be.nvls_active), "rows": rows,
                "params_sum": eng.params.double().sum().item(), "sample": eng.params[::40009].cpu().tolist()},
               open(out_json, "w"))
     be.close()

@@ -75,3 +75,13 @@ def test_interval_mode_applies_mean_of_whatever_arrived(tmp_path):
     res, _ = _run(tmp_path, ["--max_steps=5", "--interval_method=true", "--interval_ms=150"])
     a, b = res
     assert a["final_fp"] == b["final_fp"] and a["final_step"] == 6
+
+
+def test_interval_and_cdf_flags_together_do_not_deadlock(tmp_path):
+    """Both mode flags set: interval wins (reference distributed_train.py:179-183) and the cdf telemetry -- whose table
+    exchange is a collective keyed on the LOCAL iteration -- must stay off, because interval replicas are not in lock step."""
+    res, logs = _run(tmp_path, ["--max_steps=6", "--interval_method=true", "--interval_ms=100",
+                                "--worker_times_cdf_method=true"], timeout=120)
+    a, b = res
+    assert a["final_fp"] == b["final_fp"] and a["final_step"] >= 7
+    assert not any("ELAPSED TIMES" in l for l in logs)

@@ -112,6 +112,47 @@ def test_multi_rank_matches_nccl_and_masks_straggler(tmp_path):
         assert len({x["fp"] for x in rows}) == 1
 
 
+def _check_bucket_unit(res, n):
+    for s in range(5):
+        rows = [r["rows"][s] for r in res]
+        assert all(x["step"] == s + 1 and x["count"] == n and x["mask"] == (1 << n) - 1 for x in rows), rows
+        assert len({x["fp"] for x in rows}) == 1, ("replicas differ", s)          # bit-identical weights everywhere
+        assert len({x["fp_g16"] for x in rows}) == 1, ("reduced gradients differ", s)
+        assert all(x["late_err"] < 2e-6 for x in rows), rows                      # fp32 rank-ordered sum vs NCCL
+        assert all(x["fc1_bad"] == 0 for x in rows), rows                         # bf16 wire: one rounding of the sum
+        assert all(x["sum_rel_err"] < 2.0 ** -7 for x in rows), rows
+        assert all(x["shadow_err"] <= 0.01 * x["pmax"] + 1e-6 for x in rows), rows
+
+
+def test_bucket_kernels_single_replica(tmp_path):
+    """One replica: no exchange, the early kernel applies SGD to fc1 from the bf16 gradient, the late kernel the rest."""
+    worker = os.path.join(HERE, "_bucket_unit_worker.py")
+    codes = run_replicas([worker, str(tmp_path / "res_RANK.json")], 1, timeout=300, out_dir=str(tmp_path / "out"))
+    logs = "\n".join(open(os.path.join(tmp_path, "out", f)).read()[-1500:] for f in sorted(os.listdir(tmp_path / "out")))
+    assert codes == [0], logs
+    _check_bucket_unit([json.load(open(tmp_path / "res_0.json"))], 1)
+
+
+@pytest.mark.multigpu
+def test_bucket_kernels_match_nccl_oracle(tmp_path):
+    """csrc/fused_bucket.cu against NCCL directly: early bucket = in-place bf16 reduce (NVLS multimem / peer loads) + local
+    SGD, late bucket = pushed inbox + rank-ordered fp32 sum; own VMM/NVLS allocator (csrc/symm_mem.cu) and torch's."""
+    n = min(torch.cuda.device_count(), 8)
+    worker = os.path.join(HERE, "_bucket_unit_worker.py")
+    for tag, env in (("p2p", {"DMNIST_NVLS": "0"}), ("nvls_own", {"DMNIST_NVLS": "1", "DMNIST_SYMM": "own"}),
+                     ("nvls_torch", {"DMNIST_NVLS": "1", "DMNIST_SYMM": "torch"})):
+        out = tmp_path / tag
+        codes = run_replicas([worker, str(out / "res_RANK.json")], n, timeout=300, out_dir=str(out / "out"), env=env)
+        logs = "\n".join(open(os.path.join(out, "out", f)).read()[-1500:] for f in sorted(os.listdir(out / "out")))
+        assert codes == [0] * n, tag + "\n" + logs
+        res = [json.load(open(out / ("res_%d.json" % r))) for r in range(n)]
+        _check_bucket_unit(res, n)
+        if tag == "nvls_own":
+            # the product path: multicast mapping created by our own driver-API code
+            assert all(r["alloc"] == "VmmBuffer" for r in res), [r["alloc"] for r in res]
+            assert all(r["nvls"] and r["mc_ptr"] for r in res), "own NVLS multicast set-up did not come up"
+
+
 @pytest.mark.multigpu
 def test_bucketed_overlapped_aggregation_matches_single_kernel(tmp_path):
     """The bucketed path (early fc bucket next to the backward kernels + one-shot late conv bucket) must leave every
@@ -121,13 +162,15 @@ def test_bucketed_overlapped_aggregation_matches_single_kernel(tmp_path):
     worker = os.path.join(HERE, "_bucket_worker.py")
     res = {}
     for tag, env in (("bucket", {"DMNIST_BUCKET": "1", "DMNIST_NVLS": "0"}), ("single", {"DMNIST_BUCKET": "0", "DMNIST_NVLS": "0"}),
-                     ("bucket_nvls", {"DMNIST_BUCKET": "1", "DMNIST_NVLS": "1"})):
+                     ("bucket_nvls", {"DMNIST_BUCKET": "1", "DMNIST_NVLS": "1"}),
+                     ("v2", {"DMNIST_BUCKET": "2", "DMNIST_NVLS": "0"}), ("v2_nvls", {"DMNIST_BUCKET": "2", "DMNIST_NVLS": "1"})):
         out = tmp_path / tag
         codes = run_replicas([worker, str(out / "res_RANK.json"), "8"], n, timeout=300, out_dir=str(out / "out"), env=env)
         logs = "\n".join(open(os.path.join(out, "out", f)).read()[-1500:] for f in sorted(os.listdir(out / "out")))
         assert codes == [0] * n, tag + "\n" + logs
         res[tag] = [json.load(open(out / ("res_%d.json" % r))) for r in range(n)]
     assert all(r["bucketed"] for r in res["bucket"]) and not any(r["bucketed"] for r in res["single"])
+    assert all(r["bucketed"] and r["v2"] for r in res["v2"]) and all(r["v2"] for r in res["v2_nvls"])
     for tag in res:
         for s in range(8):
             rows = [r["rows"][s] for r in res[tag]]
@@ -142,4 +185,49 @@ def test_bucketed_overlapped_aggregation_matches_single_kernel(tmp_path):
     assert (first["bucket_nvls"] - first["bucket"]).abs().max().item() < 2e-6
     assert (last["bucket"] - last["single"]).abs().max().item() < 2e-2
     assert (last["bucket_nvls"] - last["bucket"]).abs().max().item() < 2e-2
+    # bf16 wire (csrc/fused_bucket.cu): fc1's gradient is rounded to bf16 before and after the reduction -> the first update
+    # differs from the fp32 path by <= lr * 2^-8 * |g|
+    assert (first["v2"] - first["single"]).abs().max().item() < 2e-5
+    assert (first["v2_nvls"] - first["v2"]).abs().max().item() < 2e-5
+    assert (last["v2"] - last["single"]).abs().max().item() < 2e-2
+    assert (last["v2_nvls"] - last["v2"]).abs().max().item() < 2e-2
     assert res["bucket"][0]["rows"][-1]["loss"] == res["bucket"][0]["rows"][-1]["loss"]      # not NaN
+
+
+def _run_interval(tmp_path, n, interval_ms, iters, delay_us):
+    worker = os.path.join(HERE, "_interval_worker.py")
+    codes = run_replicas([worker, str(tmp_path / "res_RANK.json"), str(interval_ms), str(iters), str(delay_us)], n,
+                         timeout=300, out_dir=str(tmp_path / "out"))
+    logs = "\n".join(open(os.path.join(tmp_path, "out", f)).read()[-1500:] for f in sorted(os.listdir(tmp_path / "out")))
+    assert codes == [0] * n, logs
+    return [json.load(open(tmp_path / ("res_%d.json" % r))) for r in range(n)]
+
+
+def test_interval_mode_single_replica_ticks_on_the_device_clock(tmp_path):
+    """Mode C on the device (csrc/fused_interval.cu), one replica: gradients accumulate locally, a tick applies their mean
+    when the %globaltimer deadline has passed -- ~0.2 ms per iteration and 2 ms ticks: far fewer steps than iterations."""
+    (res,) = _run_interval(tmp_path, 1, 2.0, 150, 0)
+    assert 3 <= res["steps"] <= 40, res["steps"]
+    assert res["err"] < 1e-5 * max(1.0, res["pmax"]), res["err"]
+    assert res["dropped"] == 0 and res["accepted"] == 150
+    assert all(row[2] == 1 for row in res["rows"] if row[0] > 0)          # mask = {0} on every committed tick
+    assert max(row[3] for row in res["rows"]) >= 3                        # several gradients per tick: divisor = their number
+
+
+@pytest.mark.multigpu
+def test_interval_mode_device_deadline_masks_the_late_replica(tmp_path):
+    """Several replicas free-run; the last one needs 3 ticks per iteration.  Nobody waits for it: ticks commit with the
+    replicas that have something accumulated (it is missing from those masks), its stale gradients are dropped, and all
+    replicas end with bit-identical weights = w0 - steps * lr * g."""
+    n = min(torch.cuda.device_count(), 8)
+    res = _run_interval(tmp_path, n, 2.0, 120, 6000.0)
+    steps = {r["steps"] for r in res}
+    assert len(steps) == 1 and 3 <= res[0]["steps"] <= 80, [r["steps"] for r in res]
+    assert len({r["fp"] for r in res}) == 1                               # replicas bit-identical once quiescent
+    assert all(r["err"] < 1e-5 * max(1.0, r["pmax"]) for r in res), [r["err"] for r in res]
+    assert all(r["shadow_err"] <= 0.01 * r["pmax"] + 1e-6 for r in res)
+    masks = {row[2] for r in res for row in r["rows"] if row[0] > 0}
+    late_bit = 1 << (n - 1)
+    assert any(m and not (m & late_bit) for m in masks), masks           # some tick committed without the delayed replica
+    assert res[n - 1]["dropped"] > 0                                      # ... whose stale gradients were discarded
+    assert sum(r["ticks_committed"] for r in res) == res[0]["steps"]     # every step has exactly one committer

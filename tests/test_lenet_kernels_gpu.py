@@ -58,6 +58,11 @@ def test_end_to_end_gradients_match_autograd():
     _run("check_end_to_end", B=256, seed=14)   # the benchmark batch size
 
 
+def test_bucketed_bf16_wire_step_matches_single_kernel_step():
+    _run("check_bucketed_step_matches_single_kernel")
+    _run("check_bucketed_step_matches_single_kernel", B=256, steps=4, seed=32)
+
+
 def test_training_under_cuda_graph_reduces_loss():
     _run("check_training_reduces_loss")
 

@@ -70,7 +70,7 @@ def main():
     if ctx.rank == 0:
         print(json.dumps({"n_gpus": n, "rows": rows}))
         os.makedirs("gpurun_out", exist_ok=True)
-        with open("gpurun_out/allreduce_sweep_n%d.json" % n, "w") as f:
+        with open("gpurun_out/allreduce_sweep_n%d_nvls%s.json" % (n, os.environ.get("DMNIST_NVLS", "auto")), "w") as f:
             json.dump({"n_gpus": n, "rows": rows}, f, indent=1)
     be.close()
     shutdown_context(ctx)
