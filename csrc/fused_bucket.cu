@@ -67,8 +67,12 @@ DMNIST_DEVICE float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u
 // tensor-core CTAs of the backward pass and borrow their idle issue slots (profiles/coresidency_probe_r1.txt).
 constexpr int EARLY2_THREADS = 128;
 
+// parts: bit 0 = exchange (arrival flags, in-place reduce of my shard, "shard out" flags), bit 1 = apply (wait for every
+// shard, SGD on the local fp32 master copy, bf16 shadow).  The LeNet step launches both at once; the MLP step launches the
+// exchange right after the big weight-gradient GEMM -- it touches neither weights nor shadow, so it may run next to the
+// data-gradient GEMM that still reads that layer's shadow -- and the apply after it.
 template <int NR>
-__global__ void __launch_bounds__(EARLY2_THREADS) bucket_early_kernel(SyncPeers P, SyncArgs a, BucketV2 r) {
+__global__ void __launch_bounds__(EARLY2_THREADS) bucket_early_kernel(SyncPeers P, SyncArgs a, BucketV2 r, int parts) {
   SyncCtrl* me = P.ctrl[a.rank];
   __shared__ uint32_t s_last;
   pdl_wait();
@@ -83,7 +87,7 @@ __global__ void __launch_bounds__(EARLY2_THREADS) bucket_early_kernel(SyncPeers 
     if (NR == 1) { me->t_phase_e[1] = now; me->t_phase_e[2] = now; me->t_phase_e[3] = now; me->t_phase_e[4] = now; }
   }
 
-  if (NR > 1) {
+  if (NR > 1 && (parts & 1)) {
     // ---- every rank's fc1_wgrad is complete (all-to-all flags: CTA 0 tells the peers, everybody watches the local words) ----
     if (threadIdx.x < NR) {
       if (blockIdx.x == 0) st_release_sys(&P.ctrl[threadIdx.x]->arrive_e[a.rank * 32], epoch + 1);
@@ -155,6 +159,9 @@ __global__ void __launch_bounds__(EARLY2_THREADS) bucket_early_kernel(SyncPeers 
       if (threadIdx.x < NR) st_release_sys(&P.ctrl[threadIdx.x]->done_e[a.rank * 32], epoch + 1);
       if (threadIdx.x == 0) { me->cta_counter_e = 0; me->t_phase_e[3] = globaltimer_ns(); }
     }
+  }
+  if (!(parts & 2)) return;
+  if (NR > 1) {
     if (threadIdx.x < NR) {
       const bool ok = spin_until([&] { return ld_acquire_sys(&me->done_e[threadIdx.x * 32]) >= epoch + 1; }, a.timeout_ns);
       if (!ok) me->error = 2;
@@ -218,8 +225,6 @@ __global__ void __launch_bounds__(LATE2_THREADS, 1) bucket_late_kernel(SyncPeers
     me->t_arrive[epoch % TIMING_RING] = now;     // "gradient complete" stamp: compute time excludes the barrier below
     me->t_phase[0] = now;
     if (NR == 1) me->t_phase[1] = now;
-    // K == N: the step's outcome is known before it starts -- tell the host now, the PCIe trip overlaps the exchange
-    publish_status(me, epoch + 1, me->accepted_steps + 1, me->dropped_steps, (NR >= 32) ? 0xffffffffu : ((1u << NR) - 1u), (uint32_t)NR, 0u);
   }
   const size_t half = (size_t)(epoch & 1u) * (size_t)NR * (size_t)n_late4;   // inbox half of this step (float4 units)
 
@@ -253,7 +258,11 @@ __global__ void __launch_bounds__(LATE2_THREADS, 1) bucket_late_kernel(SyncPeers
     }
     __syncthreads();
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) me->t_phase[2] = globaltimer_ns();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    me->t_phase[2] = globaltimer_ns();
+    // K == N: the outcome is known; published AFTER this CTA's fence.sys (which would otherwise wait for the PCIe store)
+    publish_status(me, epoch + 1, me->accepted_steps + 1, me->dropped_steps, (NR >= 32) ? 0xffffffffu : ((1u << NR) - 1u), (uint32_t)NR, 0u);
+  }
 
   // ---- sum the N contributions in rank order, SGD on my copy, bf16 shadow --------------------------------------------------
   const float scale = device_lr(a, epoch) / (float)NR;
@@ -285,7 +294,6 @@ __global__ void __launch_bounds__(LATE2_THREADS, 1) bucket_late_kernel(SyncPeers
   // ---- the last CTA to finish closes the step -------------------------------------------------------------------------------
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
     if (atomicAdd(&me->cta_counter2, 1u) == gridDim.x - 1) {
       const uint32_t full = (NR >= 32) ? 0xffffffffu : ((1u << NR) - 1u);
       me->last_mask = full;
@@ -300,20 +308,135 @@ __global__ void __launch_bounds__(LATE2_THREADS, 1) bucket_late_kernel(SyncPeers
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// late bucket, LL protocol (default): every 16-byte line carries its own validity tags -- {d0, tag, d1, tag}, tag = step + 1 --
+// so data and "it has arrived" travel in ONE store: no flag word, no fence.sys round trip before the flag, no grid-wide
+// barrier.  A thread multicasts its lines (multimem.st; peer stores without NVLS) and then polls the matching lines of the
+// other replicas in its own inbox until all four tags of a float4 are current.  Exposed communication = one NVLink store
+// latency (~1.5 us) instead of store + ack + flag (~7 us measured at N = 2).  The inbox is double-buffered on the step's parity
+// (a replica can be at most one step ahead of a reader) and costs 2x the bytes of the small bucket -- 475 KB per replica.
+// ---------------------------------------------------------------------------------------------------------------------
+DMNIST_DEVICE uint4 ld_volatile_b128(const void* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(LATE2_THREADS) bucket_late_ll_kernel(SyncPeers P, SyncArgs a, BucketV2 r) {
+  SyncCtrl* me = P.ctrl[a.rank];
+  pdl_wait();
+  const uint32_t epoch = me->epoch;
+  const uint32_t tag = epoch + 1;
+  const int NR = a.nranks;
+  const int early_n4 = r.fc1_e4 - r.fc1_b4;
+  const int n_late4 = r.numel4 - early_n4;
+  const int stride = gridDim.x * LATE2_THREADS;
+  const int tid = blockIdx.x * LATE2_THREADS + threadIdx.x;
+  const float* g_local = P.grads[a.rank];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const unsigned long long now = globaltimer_ns();
+    me->t_arrive[epoch % TIMING_RING] = now;     // "gradient complete" stamp: compute time excludes the exchange below
+    me->t_phase[0] = now;
+  }
+  // line index space of an inbox: [2 parities][NR slots][2 * n_late4 lines of 16 bytes]
+  const size_t lines_per_slot = 2 * (size_t)n_late4;
+  const size_t half = (size_t)(epoch & 1u) * (size_t)NR * lines_per_slot;
+
+  if (NR > 1) {
+    const size_t slot = half + (size_t)a.rank * lines_per_slot;
+    for (int j = tid; j < n_late4; j += stride) {
+      const int i = (j < r.fc1_b4) ? j : j + early_n4;
+      const float4 v = *reinterpret_cast<const float4*>(g_local + 4 * (size_t)i);
+      const uint4 l0 = make_uint4(__float_as_uint(v.x), tag, __float_as_uint(v.y), tag);
+      const uint4 l1 = make_uint4(__float_as_uint(v.z), tag, __float_as_uint(v.w), tag);
+      const size_t li = slot + 2 * (size_t)j;
+      if (r.mc_inbox != nullptr) {
+        multimem_st_b128(reinterpret_cast<uint4*>(r.mc_inbox) + li, l0);
+        multimem_st_b128(reinterpret_cast<uint4*>(r.mc_inbox) + li + 1, l1);
+      } else {
+        for (int q = 0; q < NR; ++q) {
+          if (q == a.rank) continue;
+          st_peer_b128(reinterpret_cast<uint4*>(r.inbox[q]) + li, l0);
+          st_peer_b128(reinterpret_cast<uint4*>(r.inbox[q]) + li + 1, l1);
+        }
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    me->t_phase[1] = globaltimer_ns();
+    // every line of mine is on its way; nothing below fences, so this PCIe store rides along with the exchange
+    publish_status(me, epoch + 1, me->accepted_steps + 1, me->dropped_steps, (NR >= 32) ? 0xffffffffu : ((1u << NR) - 1u), (uint32_t)NR, 0u);
+  }
+
+  // ---- receive: poll my inbox until the other replicas' lines of this step are there; rank-ordered sum; SGD; shadow -------
+  const float scale = device_lr(a, epoch) / (float)NR;
+  float* wdst = P.params[a.rank];
+  const uint4* inbox = reinterpret_cast<const uint4*>(r.inbox[a.rank]);
+  for (int j = tid; j < n_late4; j += stride) {
+    const int i = (j < r.fc1_b4) ? j : j + early_n4;
+    const float4 own = *reinterpret_cast<const float4*>(g_local + 4 * (size_t)i);
+    float4 g[SYNC_MAX_RANKS];
+#pragma unroll
+    for (int c = 0; c < SYNC_MAX_RANKS; ++c) {
+      if (c >= NR) continue;
+      if (c == a.rank) { g[c] = own; continue; }
+      const uint4* src = inbox + half + (size_t)c * lines_per_slot + 2 * (size_t)j;
+      uint4 l0, l1;
+      const bool ok = spin_until([&] {
+        l0 = ld_volatile_b128(src);
+        l1 = ld_volatile_b128(src + 1);
+        return l0.y == tag && l0.w == tag && l1.y == tag && l1.w == tag;
+      }, a.timeout_ns);
+      if (!ok) me->error = 1;
+      g[c] = make_float4(__uint_as_float(l0.x), __uint_as_float(l0.z), __uint_as_float(l1.x), __uint_as_float(l1.z));
+    }
+    float4 nw = *reinterpret_cast<const float4*>(wdst + 4 * (size_t)i);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < SYNC_MAX_RANKS; ++c)
+      if (c < NR) { acc.x += g[c].x; acc.y += g[c].y; acc.z += g[c].z; acc.w += g[c].w; }
+    nw.x -= scale * acc.x; nw.y -= scale * acc.y; nw.z -= scale * acc.z; nw.w -= scale * acc.w;
+    *reinterpret_cast<float4*>(wdst + 4 * (size_t)i) = nw;
+    if (a.shadow != nullptr) {
+      uint2 o;
+      o.x = pack_bf16x2(nw.x, nw.y);
+      o.y = pack_bf16x2(nw.z, nw.w);
+      *reinterpret_cast<uint2*>(a.shadow + 4 * (size_t)i) = o;
+    }
+  }
+  // ---- the last CTA to finish closes the step -------------------------------------------------------------------------------
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(&me->cta_counter2, 1u) == gridDim.x - 1) {
+      const uint32_t full = (NR >= 32) ? 0xffffffffu : ((1u << NR) - 1u);
+      me->last_mask = full;
+      me->last_count = NR;
+      me->last_late = 0;
+      me->accepted_steps += 1;
+      me->cta_counter2 = 0;
+      const unsigned long long now = globaltimer_ns();
+      me->t_phase[2] = now; me->t_phase[3] = now; me->t_phase[4] = now; me->t_phase[5] = now;
+      me->epoch = epoch + 1;
+    }
+  }
+}
+
 }  // namespace dm
 
 extern "C" {
 
-// phase 1 = early bucket (fc1 weights, bf16 wire, side branch), phase 2 = late bucket + end of the step.
+// phase 1 = early bucket (the big weight matrix, bf16 wire, side branch): exchange + apply; 3 = exchange only; 4 = apply only;
+// phase 2 = late bucket + end of the step.
 //   ctrl/params/grads: tables of `nranks` peer pointers (index = rank);  g16 / inbox: same, for the bf16 fc1 gradient buffer
-//   and the late-bucket inbox (2 * nranks * (numel - fc1 numel) floats);  mc_*: NVLS multicast views or null.
+//   and the late-bucket inbox (2 parities x nranks slots x (numel - fc1 numel) x 8 bytes: LL lines);  mc_*: NVLS multicast views
+//   or null;  late_ll: 1 = LL protocol for the late bucket (default), 0 = data + release flags.
 //   fc1_begin/fc1_end/numel in floats, all multiples of 8 / 8 / 4.
 int dm_bucket_sync(void* const* ctrl, void* const* params, void* const* grads, void* const* g16, void* const* inbox, int rank,
                    int nranks, int phase, long long fc1_begin, long long fc1_end, long long numel, float lr0,
                    float decay_rate, int decay_steps, double timeout_ms, void* shadow_bf16, int ctas, void* stream_,
-                   void* mc_g16, void* mc_inbox) {
+                   void* mc_g16, void* mc_inbox, int late_ll) {
   using namespace dm;
-  if (nranks < 1 || nranks > SYNC_MAX_RANKS || phase < 1 || phase > 2) return -1;
+  if (nranks < 1 || nranks > SYNC_MAX_RANKS || phase < 1 || phase > 4) return -1;
   if ((fc1_begin & 7) || (fc1_end & 7) || (numel & 3) || fc1_begin < 0 || fc1_end < fc1_begin || fc1_end > numel) return -2;
   SyncPeers P;
   BucketV2 r;
@@ -343,21 +466,27 @@ int dm_bucket_sync(void* const* ctrl, void* const* params, void* const* grads, v
     DM_CUDA_OK(cudaFuncSetAttribute(bucket_early_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     DM_CUDA_OK(cudaFuncSetAttribute(bucket_early_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     DM_CUDA_OK(cudaFuncSetAttribute(bucket_late_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    DM_CUDA_OK(cudaFuncSetAttribute(bucket_late_ll_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
-  if (phase == 1) {
+  if (phase != 2) {
     if (ctas < 1) ctas = 148;
     const dim3 g(ctas), b(EARLY2_THREADS);
-    if (nranks == 1) return (int)launch_kernel(bucket_early_kernel<1>, g, b, 0, stream, P, a, r);
-    if (nranks == 2) return (int)launch_kernel(bucket_early_kernel<2>, g, b, 0, stream, P, a, r);
-    if (nranks == 4) return (int)launch_kernel(bucket_early_kernel<4>, g, b, 0, stream, P, a, r);
-    if (nranks == 8) return (int)launch_kernel(bucket_early_kernel<8>, g, b, 0, stream, P, a, r);
+    const int parts = phase == 1 ? 3 : (phase == 3 ? 1 : 2);
+    if (nranks == 1) return (int)launch_kernel(bucket_early_kernel<1>, g, b, 0, stream, P, a, r, parts);
+    if (nranks == 2) return (int)launch_kernel(bucket_early_kernel<2>, g, b, 0, stream, P, a, r, parts);
+    if (nranks == 4) return (int)launch_kernel(bucket_early_kernel<4>, g, b, 0, stream, P, a, r, parts);
+    if (nranks == 8) return (int)launch_kernel(bucket_early_kernel<8>, g, b, 0, stream, P, a, r, parts);
     return -5;    // instantiated for 1, 2, 4 and 8 replicas; the caller falls back to the single kernel
   }
   if (nranks > 1 && inbox == nullptr) return -3;
   const int n_late4 = r.numel4 - (r.fc1_e4 - r.fc1_b4);
   int grid = (n_late4 + LATE2_THREADS - 1) / LATE2_THREADS;      // one float4 per thread: a single round of loads
   if (grid < 1) grid = 1;
+  if (late_ll) {                                                  // no in-kernel barrier: any grid size is safe
+    if (grid > 296) grid = 296;
+    return (int)launch_kernel(bucket_late_ll_kernel, dim3(grid), dim3(LATE2_THREADS), 0, stream, P, a, r);
+  }
   if (ctas >= 1 && grid > ctas) grid = ctas;
   if (grid > 148) grid = 148;                                     // all CTAs must be co-resident (in-kernel barrier)
   return (int)launch_kernel(bucket_late_kernel, dim3(grid), dim3(LATE2_THREADS), 0, stream, P, a, r);

@@ -125,7 +125,15 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_sgd_kernel(SyncPee
       }
     }
   } else {
-    if (blockIdx.x == 0 && threadIdx.x < 32) decide<KOFN>(P, a, me, epoch);
+    // The arrival / commit decision is taken by whichever CTA gets here first (its warp 0), not by a fixed block index:
+    // CUDA does not promise that block 0 is resident before the polling CTAs fill the machine (side-stream kernels or an
+    // evaluator sharing the GPU may hold SMs), and every other CTA only spins on a LOCAL word.
+    if (threadIdx.x < 32) {
+      uint32_t won = 0;
+      if (threadIdx.x == 0) won = atomicMax(&me->decider_claim, epoch + 1) < epoch + 1 ? 1u : 0u;
+      won = __shfl_sync(0xffffffffu, won, 0);
+      if (won) decide<KOFN>(P, a, me, epoch);
+    }
     if (threadIdx.x == 0) {
       spin_until([&] { return ld_acquire_sys(&me->decided_tag) == epoch + 1; }, a.timeout_ns * 2);
       s_mask = me->decided_mask;
@@ -541,7 +549,7 @@ int dm_sync_ctrl_offset(const char* field) {
   DM_OFF(cta_counter); DM_OFF(t_phase); DM_OFF(t_phase_e); DM_OFF(arrive); DM_OFF(done); DM_OFF(arrive_e); DM_OFF(done_e);
   DM_OFF(commit_local); DM_OFF(bitmap); DM_OFF(commit); DM_OFF(last_in_mask); DM_OFF(decided_tag); DM_OFF(decided_mask);
   DM_OFF(decided_late); DM_OFF(decided_target); DM_OFF(cta_counter_e); DM_OFF(cta_counter2);
-  DM_OFF(status_seq); DM_OFF(host_mirror); DM_OFF(iv_state); DM_OFF(iv_busy); DM_OFF(iv_deadline); DM_OFF(iv_ticks_committed);
+  DM_OFF(status_seq); DM_OFF(host_mirror); DM_OFF(decider_claim); DM_OFF(iv_state); DM_OFF(iv_busy); DM_OFF(iv_deadline); DM_OFF(iv_ticks_committed);
 #undef DM_OFF
   return -1;
 }

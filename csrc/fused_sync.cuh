@@ -68,7 +68,8 @@ struct SyncCtrl {
   // outcome without a device read or a memcpy node in the step graph (a D2H memcpy node costs the graph ~10 us) ------------------
   uint32_t status_seq;                     // number of steps closed so far (ring index of the mirror slot = seq & 3)
   uint32_t* host_mirror;                   // 4 slots x 8 words in mapped pinned host memory, or null
-  uint32_t pad3[16];
+  uint32_t decider_claim;                  // step+1 of the newest launch whose arrival/commit decision a CTA has claimed
+  uint32_t pad3[15];
 };
 
 struct SyncPeers {

@@ -262,9 +262,9 @@ class CudaLeNetEngine(ComputeEngine):
             e0, e1 = self._bucket_early
             assert e0 % 8 == 0 and (e1 - e0) % 8 == 0, "fc1 weights must start on a 32-byte boundary of the arena"
             self._g16 = self.backend.allocate_buffer((e1 - e0) * 2)
-            self._g16_view = self._g16.view(torch.bfloat16, 0, e1 - e0).view(3136, 512)
+            self._g16_view = self._g16.view(torch.bfloat16, 0, e1 - e0).view(*getattr(self, "_g16_shape", (3136, 512)))
             n_late = self.spec.arena_numel - (e1 - e0)
-            self._inbox = self.backend.allocate_buffer(2 * n * n_late * 4) if n > 1 else None
+            self._inbox = self.backend.allocate_buffer(2 * n * n_late * 8) if n > 1 else None   # LL lines: 8 bytes per float
         self._early_ctas = int(os.environ.get("DMNIST_EARLY_CTAS", "148"))
         torch.cuda.synchronize()
         self._seq0 = self.backend.status_seq       # steps closed on this control block before the engine's first one
@@ -640,6 +640,17 @@ class CudaMlpEngine(ComputeEngine):
         self._opt_args: Optional[dict] = None
         self._straggler = None
         self.launches_per_step = 0
+        # bucketed aggregation (csrc/fused_bucket.cu): the largest weight matrix is the early bucket (bf16 wire, exchanged next
+        # to the remaining backward GEMMs), everything else the pushed late bucket
+        big = max((q for q in self.spec.params if q.name.endswith("weights")), key=lambda q: q.numel)
+        self._early_name = big.name
+        self._bucket_split = big.offset
+        self._bucket_early = (big.offset, big.offset + big.numel)
+        self._g16_shape = (784 if big.name == "fc1_weights" else hidden, hidden if big.name != "fc%d_weights" % self.n_layers else 10)
+        self._branches = True
+        self._bucketed = self._bucket_v2 = False
+        self._g16 = self._g16_view = self._inbox = None
+        self._side = [torch.cuda.Stream(device=dev)]
         # everything except the weight matrices (written whole by GEMM stores) is accumulated with atomics
         stored = sorted((q.offset, q.offset + q.numel) for q in self.spec.params if q.name.endswith("weights"))
         self._zero_ranges, pos = [], 0
@@ -689,9 +700,15 @@ class CudaMlpEngine(ComputeEngine):
                                   ptr(self.d_loss_acc), ptr(logits_out), B, H, int(train), sp), "dense10_xent")
         return n + 2
 
-    def _backward(self, B: int) -> int:
+    def _backward(self, B: int, early_sync: bool = False) -> int:
+        """``early_sync``: bucketed aggregation -- the big layer's weight gradient is stored as bf16 into the wire buffer and its
+        exchange (phase 3) starts on a side stream at once, next to the data-gradient GEMM; the apply (phase 4) follows that
+        GEMM, which is the last reader of the layer's bf16 shadow."""
         lib, sp, g, pb, H, L = self.lib, stream_ptr(), self.g, self.pb, self.hidden, self.n_layers
         n = 0
+        main = torch.cuda.current_stream()
+        oa, be = self._opt_args, self.backend
+        self._join_early = None
         # output layer: dW_L[H,10] = h_last^T (MN-major) * dl (MN-major, 64-wide zero-padded rows, N = 10)
         G.gemm_bf16_raw(self.h[-1], self.dl_pad, g["fc%d_weights" % L], H, 10, B, H, 64, 10, True, True,
                         G.EPI_STORE_F32, bn=64)
@@ -700,17 +717,45 @@ class CudaMlpEngine(ComputeEngine):
         n += 2
         for i in range(L - 1, 0, -1):
             src, K = (self.h[i - 2], H) if i > 1 else (self.x16, 784)
+            early = early_sync and self._early_name == "fc%d_weights" % i
             # dW_i[in,H] = src^T (MN-major) * dh_i (MN-major), K = batch
-            G.gemm_bf16_raw(src, self.dh[i - 1], g["fc%d_weights" % i], K, H, B, K, H, H, True, True,
-                            G.EPI_STORE_F32, bn=128)
+            if early:
+                G.gemm_bf16_raw(src, self.dh[i - 1], self._g16_view, K, H, B, K, H, H, True, True, G.EPI_STORE_BF16, bn=128)
+                e0, e1 = self._bucket_early
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side = self._side[0]
+                side.wait_event(ev)
+                be.enqueue_bucket_v2(self.params, self.grads, self._g16, self._inbox, 3 if i > 1 else 1, e0, e1, oa["lr0"],
+                                     oa["decay_rate"], oa["decay_steps"], stream=side)
+                n += 1
+                if i == 1:
+                    self._join_early = torch.cuda.Event()
+                    self._join_early.record(side)
+            else:
+                G.gemm_bf16_raw(src, self.dh[i - 1], g["fc%d_weights" % i], K, H, B, K, H, H, True, True,
+                                G.EPI_STORE_F32, bn=128)
             n += 1
             if i > 1:
                 # dh_{i-1} = (dh_i @ W_i^T) * relu'(h_{i-1});  W_i [in,out]: rows = in (N), K = out contiguous
                 G.gemm_bf16_raw(self.dh[i - 1], pb["fc%d_weights" % i], self.dh[i - 2], B, H, H, H, H, H, False, False,
                                 G.EPI_STORE_BF16, bn=128)
+                if early:
+                    # the data-gradient GEMM above was the last reader of this layer's bf16 shadow: the apply may rewrite it
+                    ev2 = torch.cuda.Event()
+                    ev2.record(main)
+                    side = self._side[0]
+                    side.wait_event(ev2)
+                    be.enqueue_bucket_v2(self.params, self.grads, self._g16, self._inbox, 4, e0, e1, oa["lr0"],
+                                         oa["decay_rate"], oa["decay_steps"], stream=side)
+                    n += 1
+                    self._join_early = torch.cuda.Event()
+                    self._join_early.record(side)
                 check(lib.dm_relu_bwd_colsum(ptr(self.dh[i - 2]), ptr(self.h[i - 2]), ptr(self.dh[i - 2]),
                                              ptr(g["fc%d_biases" % (i - 1)]), B, H, sp), "relu_bwd_colsum")
                 n += 2
+        if self._join_early is not None:
+            main.wait_event(self._join_early)
         return n
 
     def _launch_zero(self) -> int:
@@ -727,10 +772,20 @@ class CudaMlpEngine(ComputeEngine):
         if interval:
             self.backend.enqueue_interval_begin(self.params)
             n += 2
+        bucketed = with_sync and self._bucket_v2 and not interval
         n += self._launch_zero()
         n += self._forward(self.images[slot], self.labels[slot], B, True)
-        n += self._backward(B)
-        if with_sync:
+        n += self._backward(B, early_sync=bucketed)
+        if bucketed:
+            if self._straggler is not None:
+                self.backend.enqueue_straggler_delay(self._straggler.prob, self._straggler.usec)
+                n += 1
+            oa = self._opt_args
+            e0, e1 = self._bucket_early
+            self.backend.enqueue_bucket_v2(self.params, self.grads, self._g16, self._inbox, 2, e0, e1, oa["lr0"],
+                                           oa["decay_rate"], oa["decay_steps"])
+            n += 1
+        elif with_sync:
             if self._straggler is not None:
                 self.backend.enqueue_straggler_delay(self._straggler.prob, self._straggler.usec)
                 n += 1

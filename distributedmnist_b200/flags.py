@@ -216,7 +216,7 @@ def define_reference_flags(F: FlagValues = FLAGS) -> FlagValues:
     # reference: src/distributed_train.py:68-78
     F.DEFINE_integer("task_id", 0, "Replica index; replica 0 is the chief")
     F.DEFINE_integer("num_replicas_to_aggregate", -1, "Gradients to collect before updating (K of N); -1 = all")
-    F.DEFINE_integer("save_interval_secs", 20, "Checkpoint interval in seconds (chief)")
+    F.DEFINE_float("save_interval_secs", 20, "Checkpoint interval in seconds (chief); fractions allowed: a B200 step is ~0.1 ms")
     F.DEFINE_integer("save_summaries_secs", 300, "Summary interval in seconds (chief)")
     # reference: src/distributed_train.py:92-98
     F.DEFINE_float("initial_learning_rate", 0.1, "Initial learning rate")
@@ -228,7 +228,7 @@ def define_reference_flags(F: FlagValues = FLAGS) -> FlagValues:
     # reference: src/nn_eval.py:36-45
     F.DEFINE_string("eval_dir", "/tmp/imagenet_eval", "Directory where the evaluator writes its event log")
     F.DEFINE_string("checkpoint_dir", "/tmp/imagenet_train", "Directory the evaluator polls for checkpoints")
-    F.DEFINE_integer("eval_interval_secs", 1, "How often the evaluator polls")
+    F.DEFINE_float("eval_interval_secs", 1, "How often the evaluator polls (seconds, fractions allowed)")
     F.DEFINE_boolean("run_once", False, "Evaluate once and exit")
     return F
 

@@ -240,7 +240,8 @@ def check_end_to_end(B: int = 64, seed: int = 5) -> List[Result]:
     return out
 
 
-def check_bucketed_step_matches_single_kernel(B: int = 64, steps: int = 6, seed: int = 31) -> List[Result]:
+def check_bucketed_step_matches_single_kernel(B: int = 64, steps: int = 6, seed: int = 31, model: str = "lenet",
+                                              hidden: int = 256) -> List[Result]:
     """One replica, whole graph-replayed training steps: bucketed aggregation (csrc/fused_bucket.cu: fc1 gradient as bf16,
     applied by the early kernel under the backward pass; small bucket by the late kernel) vs the single fused kernel."""
     import os
@@ -254,7 +255,12 @@ def check_bucketed_step_matches_single_kernel(B: int = 64, steps: int = 6, seed:
     try:
         for mode in ("2", "0"):
             os.environ["DMNIST_BUCKET"] = mode
-            eng, be = _engine(B, seed)
+            if model == "lenet":
+                eng, be = _engine(B, seed)
+            else:
+                from ..engine_cuda import CudaMlpEngine
+                be = FusedBackend(ReplicaContext(0, 1, 0, torch.device("cuda", 0), "none"))
+                eng = CudaMlpEngine(model, B, be, hidden=hidden, seed=seed, use_graph=True)
             eng.use_graph = True
             eng.attach_optimizer(SyncReplicasOptimizer(be, LearningRateSchedule(0.05, 2, 0.5), 1, 1))
             losses = []
@@ -282,13 +288,19 @@ def check_bucketed_step_matches_single_kernel(B: int = 64, steps: int = 6, seed:
     # dropout decisions, so the final comparison is loose
     upd = (f0 - i0).abs()
     first_excess = ((f2 - f0).abs() - (upd * 2.0 ** -8 + 1e-6 * pmax)).max().item()
-    return [("bucket_v2.enabled", 0.0 if (v2 and not v0) else 1.0, 0.5),
-            ("bucket_v2.steps", abs(st2 - steps) + abs(st0 - steps), 0.5),
-            ("bucket_v2.first_step_excess", max(first_excess, 0.0) / pmax, 1e-6),
-            ("bucket_v2.first_update(rel, info)", upd.max().item() / pmax, 1e9),
-            ("bucket_v2.params_vs_single(rel)", (p2 - p0).abs().max().item() / pmax, 0.05),
-            ("bucket_v2.shadow(rel)", (s2 - p2).abs().max().item() / pmax, 0.01),
-            ("bucket_v2.loss", max(abs(a - b) for a, b in zip(l2, l0)), 0.02)]
+    tag = "bucket_v2" if model == "lenet" else "bucket_v2.%s" % model
+    return [(tag + ".enabled", 0.0 if (v2 and not v0) else 1.0, 0.5),
+            (tag + ".steps", abs(st2 - steps) + abs(st0 - steps), 0.5),
+            (tag + ".first_step_excess", max(first_excess, 0.0) / pmax, 1e-6),
+            (tag + ".first_update(rel, info)", upd.max().item() / pmax, 1e9),
+            (tag + ".params_vs_single(rel)", (p2 - p0).abs().max().item() / pmax, 0.05),
+            (tag + ".shadow(rel)", (s2 - p2).abs().max().item() / pmax, 0.01),
+            (tag + ".loss", max(abs(a - b) for a, b in zip(l2, l0)), 0.02)]
+
+
+def check_bucketed_mlp_step_matches_single_kernel() -> List[Result]:
+    return (check_bucketed_step_matches_single_kernel(B=128, steps=4, seed=41, model="mlp3", hidden=256)
+            + check_bucketed_step_matches_single_kernel(B=96, steps=3, seed=42, model="mlp2", hidden=128))
 
 
 def check_training_reduces_loss(B: int = 128, steps: int = 40) -> List[Result]:
@@ -346,4 +358,5 @@ def check_mlp2_end_to_end() -> List[Result]:
 
 
 ALL_CHECKS = [check_conv1_fwd, check_conv1_fwd_tc, check_conv1_wgrad, check_conv1_wgrad_simt, check_conv2_fwd, check_conv2_dgrad, check_conv2_wgrad, check_fc2_loss, check_fc1_dgrad_unpool,
-              check_end_to_end, check_bucketed_step_matches_single_kernel, check_training_reduces_loss, check_mlp_end_to_end, check_mlp2_end_to_end]
+              check_end_to_end, check_bucketed_step_matches_single_kernel, check_bucketed_mlp_step_matches_single_kernel,
+              check_training_reduces_loss, check_mlp_end_to_end, check_mlp2_end_to_end]

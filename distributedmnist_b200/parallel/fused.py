@@ -61,12 +61,13 @@ class FusedBackend(Backend):
                       "global_step", "t_arrive", "t_start", "cta_counter", "t_phase", "t_phase_e", "arrive", "done",
                       "arrive_e", "done_e", "commit_local", "bitmap", "commit", "last_in_mask", "decided_tag",
                       "decided_mask", "decided_late", "decided_target", "cta_counter_e", "cta_counter2", "status_seq",
-                      "host_mirror", "iv_state", "iv_busy", "iv_deadline", "iv_ticks_committed")}
+                      "host_mirror", "iv_state", "iv_busy", "iv_deadline", "iv_ticks_committed", "decider_claim")}
         assert all(v >= 0 for v in self._off.values()), self._off
         # the host-readable status words (epoch .. last_late) sit next to each other: ONE device->host copy per query
         self._status_lo = min(self._off[f] for f in self._STATUS)
         self._status_hi = max(self._off[f] for f in self._STATUS) + 4
         self.debug_sync = debug_sync or os.environ.get("DMNIST_DEBUG_SYNC", "0") == "1"
+        self.late_ll = os.environ.get("DMNIST_LATE_LL", "1") != "0"     # LL lines (data + tags in one store) for the late bucket
         # host mirror of the status words: the kernel that closes a step stores them into page-locked host memory itself
         self._mirror = torch.zeros(4 * 8, dtype=torch.int32).pin_memory()
         check(self.lib.dm_sync_set_host_mirror(ctypes.c_void_p(self.ctrl.local_ptr), ctypes.c_void_p(self._mirror.data_ptr())),
@@ -119,6 +120,7 @@ class FusedBackend(Backend):
         """Checkpoint restore: every rank starts from ``step`` (also the chief's commit counter)."""
         self._write_u32("epoch", step)
         self._write_u32("global_step", step)
+        self._write_u32("decider_claim", step)
         torch.cuda.synchronize()
         self.barrier()
 
@@ -253,7 +255,7 @@ class FusedBackend(Backend):
             ctypes.c_longlong(fc1_begin), ctypes.c_longlong(fc1_end), ctypes.c_longlong(params.numel()),
             ctypes.c_float(lr0), ctypes.c_float(decay_rate), int(decay_steps), ctypes.c_double(self.timeout_ms),
             ctypes.c_void_p(0 if self.shadow is None else self.shadow.data_ptr()), int(ctas), stream_ptr(stream),
-            ctypes.c_void_p(mc_g16), ctypes.c_void_p(mc_inbox))
+            ctypes.c_void_p(mc_g16), ctypes.c_void_p(mc_inbox), int(self.late_ll))
         check(rc, "dm_bucket_sync(phase %d)" % phase)
 
     # ---- device-side interval mode (mode C, csrc/fused_interval.cu) ----------------------------------------------------------

@@ -156,7 +156,10 @@ class _FdChannel:
         return self._tag
 
     def send(self, fd: int, to: int, tag: int) -> None:
-        socket.send_fds(self.sock, [struct.pack("ii", tag, self.rank)], [fd], 0, self._addr(to))
+        # (socket.send_fds() drops its `address` argument in CPython <= 3.12, so the ancillary message is built here)
+        import array
+        self.sock.sendmsg([struct.pack("ii", tag, self.rank)],
+                          [(socket.SOL_SOCKET, socket.SCM_RIGHTS, array.array("i", [fd]))], 0, self._addr(to))
 
     def recv(self, frm: int, tag: int) -> int:
         while (tag, frm) not in self._pending:

@@ -49,8 +49,9 @@ LOG_FORMAT = ("Worker %d: %s: step %d, loss = %f, train_acc = %f, test_acc = %f"
 class _AsyncCheckpointer:
     """Chief-side saver: snapshot on the training thread, file IO on a helper thread."""
 
-    def __init__(self, train_dir: str, spec, interval_s: float):
+    def __init__(self, train_dir: str, spec, interval_s: float, step_fn=None):
         self.train_dir, self.spec, self.interval_s = train_dir, spec, interval_s
+        self.step_fn = step_fn       # GPU path: drain the step in flight and read the device step counter (consistent snapshot)
         self.saver = Saver()
         self._next = time.time() + interval_s
         self._thread: Optional[threading.Thread] = None
@@ -61,6 +62,8 @@ class _AsyncCheckpointer:
             self.save(params, global_step, blocking=False)
 
     def save(self, params: torch.Tensor, global_step: int, blocking: bool = True) -> None:
+        if self.step_fn is not None:
+            global_step = self.step_fn()         # the host loop runs one step ahead of what it has consumed
         state = self.spec.to_state_dict(params)  # consistent snapshot (device -> host copy)
         if self._thread is not None:
             self._thread.join()
@@ -173,7 +176,12 @@ def train(ctx: ReplicaContext, dataset, dataset_test=None, flags=FLAGS) -> Dict:
         engine.params_updated()
     log.info("%s Supervisor" % datetime.now())
 
-    ckpt = _AsyncCheckpointer(flags.train_dir, spec, flags.save_interval_secs) if is_chief else None
+    def _device_step() -> int:
+        torch.cuda.synchronize()
+        return int(backend.device_epoch)
+    ckpt = _AsyncCheckpointer(flags.train_dir, spec, flags.save_interval_secs,
+                              step_fn=_device_step if (fused_step and hasattr(backend, "device_epoch")) else None) \
+        if is_chief else None
     summary = SummaryWriter(flags.train_dir) if (is_chief and flags.should_summarize) else None
 
     # Even if not using timeout, we want to wait until all machines are ready (reference :275-277).

@@ -85,3 +85,19 @@ def test_interval_and_cdf_flags_together_do_not_deadlock(tmp_path):
     a, b = res
     assert a["final_fp"] == b["final_fp"] and a["final_step"] >= 7
     assert not any("ELAPSED TIMES" in l for l in logs)
+
+
+def test_fd_channel_passes_descriptors_between_ranks(tmp_path):
+    """The fd exchange behind the VMM / NVLS-multicast allocator (parallel/symm_mem.py): SCM_RIGHTS over abstract AF_UNIX
+    datagram sockets, all-to-all and broadcast, plus the collective AND that keeps the ranks on the same branch."""
+    worker = os.path.join(HERE, "_fdchannel_worker.py")
+    n = 3
+    codes = run_replicas([worker, str(tmp_path / "res_RANK.json")], n, timeout=120, out_dir=str(tmp_path / "out"))
+    logs = "\n".join(open(os.path.join(tmp_path, "out", f)).read()[-1500:] for f in sorted(os.listdir(tmp_path / "out")))
+    assert codes == [0] * n, logs
+    res = [json.load(open(tmp_path / ("res_%d.json" % r))) for r in range(n)]
+    for r in range(n):
+        for row in res[r]["texts"]:
+            assert row == ["self" if q == r else "hello from rank %d" % q for q in range(n)], row
+        assert res[r]["bcast"] == "hello from rank 0"
+        assert res[r]["all_ok"] is False

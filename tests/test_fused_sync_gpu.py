@@ -231,3 +231,18 @@ def test_interval_mode_device_deadline_masks_the_late_replica(tmp_path):
     assert any(m and not (m & late_bit) for m in masks), masks           # some tick committed without the delayed replica
     assert res[n - 1]["dropped"] > 0                                      # ... whose stale gradients were discarded
     assert sum(r["ticks_committed"] for r in res) == res[0]["steps"]     # every step has exactly one committer
+
+
+@pytest.mark.multigpu
+def test_message_passing_litmus_over_nvlink_and_nvls(tmp_path):
+    """The ordering pattern of every aggregation kernel, 20 000 rounds inside one launch on two GPUs: weak stores ->
+    bar.sync -> fence.sys + st.release.sys(flag on the peer) || ld.acquire.sys(flag) -> bar.sync -> peer loads and
+    multimem.ld_reduce of the data.  Any stale value is a violation."""
+    worker = os.path.join(HERE, "_litmus_worker.py")
+    codes = run_replicas([worker, str(tmp_path / "res_RANK.json"), "20000"], 2, timeout=300, out_dir=str(tmp_path / "out"))
+    logs = "\n".join(open(os.path.join(tmp_path, "out", f)).read()[-1500:] for f in sorted(os.listdir(tmp_path / "out")))
+    assert codes == [0, 0], logs
+    w, r = (json.load(open(tmp_path / ("res_%d.json" % q))) for q in range(2))
+    assert not w["aborted"] and not r["aborted"], (w, r)
+    assert w["rounds"] == 20000 and r["rounds"] == 20000, (w, r)
+    assert r["bad_p2p"] == 0 and r["bad_mc"] == 0, r

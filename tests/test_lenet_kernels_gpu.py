@@ -63,6 +63,10 @@ def test_bucketed_bf16_wire_step_matches_single_kernel_step():
     _run("check_bucketed_step_matches_single_kernel", B=256, steps=4, seed=32)
 
 
+def test_bucketed_mlp_step_matches_single_kernel_step():
+    _run("check_bucketed_mlp_step_matches_single_kernel")
+
+
 def test_training_under_cuda_graph_reduces_loss():
     _run("check_training_reduces_loss")
 
