@@ -531,6 +531,20 @@ __global__ void straggler_delay_kernel(const SyncCtrl* ctrl, float prob, unsigne
   }
 }
 
+// Device-side barrier over NVLink flags: returns on every replica within a flag hop (~2 us) of the LAST replica entering it.
+// Used to align the replicas' streams (e.g. right before a timed region: a host-side barrier leaves tens of microseconds of
+// start skew between the processes).
+__global__ void device_barrier_kernel(SyncPeers P, int rank, int nranks, unsigned long long timeout_ns) {
+  SyncCtrl* me = P.ctrl[rank];
+  const uint32_t seq = me->bar_seq + 1;
+  if (threadIdx.x < nranks) {
+    st_release_sys(&P.ctrl[threadIdx.x]->bar[rank * 32], seq);
+    if (!spin_until([&] { return ld_acquire_sys(&me->bar[threadIdx.x * 32]) >= seq; }, timeout_ns)) me->error = 1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) me->bar_seq = seq;
+}
+
 // Stamp the start of a step's compute (%globaltimer) for the cdf-mode telemetry.
 __global__ void stamp_start_kernel(SyncCtrl* ctrl) { ctrl->t_start[ctrl->epoch % TIMING_RING] = globaltimer_ns(); }
 
@@ -654,6 +668,19 @@ int dm_f32_to_bf16(const void* src, void* dst, long long numel, void* stream_) {
 int dm_straggler_delay(const void* ctrl, float prob, unsigned int usec, unsigned int seed, void* stream_) {
   dm::straggler_delay_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
       reinterpret_cast<const dm::SyncCtrl*>(ctrl), prob, usec, seed);
+  return (int)cudaGetLastError();
+}
+
+int dm_device_barrier(void* const* ctrl, int rank, int nranks, double timeout_ms, void* stream_) {
+  using namespace dm;
+  if (nranks < 1 || nranks > SYNC_MAX_RANKS) return -1;
+  SyncPeers P;
+  for (int i = 0; i < SYNC_MAX_RANKS; ++i) {
+    P.ctrl[i] = reinterpret_cast<SyncCtrl*>(ctrl[i < nranks ? i : rank]);
+    P.params[i] = nullptr;
+    P.grads[i] = nullptr;
+  }
+  device_barrier_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(P, rank, nranks, (unsigned long long)(timeout_ms * 1e6));
   return (int)cudaGetLastError();
 }
 

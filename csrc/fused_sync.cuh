@@ -69,7 +69,9 @@ struct SyncCtrl {
   uint32_t status_seq;                     // number of steps closed so far (ring index of the mirror slot = seq & 3)
   uint32_t* host_mirror;                   // 4 slots x 8 words in mapped pinned host memory, or null
   uint32_t decider_claim;                  // step+1 of the newest launch whose arrival/commit decision a CTA has claimed
-  uint32_t pad3[15];
+  uint32_t bar_seq;                        // device barriers completed so far (dm_device_barrier)
+  uint32_t pad3[14];
+  volatile uint32_t bar[SYNC_MAX_RANKS * 32];   // [p*32]: peer p entered device barrier number (value)
 };
 
 struct SyncPeers {

@@ -5,8 +5,8 @@
 // every SM with one CTA of a given shape (dynamic shared memory, registers per thread, threads) and spins, then a
 // "guest" kernel on another stream, and reports when the guest's CTAs actually started: during the residents'
 // lifetime (co-resident) or only after they exited.
-#include "common.cuh"
-#include "host_utils.h"
+#include "../common.cuh"
+#include "../host_utils.h"
 
 namespace dm {
 

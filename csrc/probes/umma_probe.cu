@@ -6,8 +6,8 @@
 // TMA; for every row shift r the kernel multiplies rows [r, r+128) by a 64x64 (or 32-wide K) matrix B and
 // writes D.  mode 0: base_offset = 0;  mode 1: base_offset = (start_address >> 7) & 7.
 // The host compares with the exact product, so the result table says which encoding the hardware expects.
-#include "common.cuh"
-#include "host_utils.h"
+#include "../common.cuh"
+#include "../host_utils.h"
 
 namespace dm {
 

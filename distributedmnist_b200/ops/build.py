@@ -85,5 +85,26 @@ def build(force: bool = False, verbose: bool = True) -> str:
     return LIB_PATH
 
 
+PROBE_DIR = os.path.join(CSRC, "probes")
+PROBE_LIB_PATH = os.path.join(LIB_DIR, "libdmnist_probes.so")
+
+
+def build_probes() -> str:
+    """Bring-up probes (csrc/probes/*.cu: UMMA descriptor row-shift probe, SM co-residency probe) as their OWN library --
+    they are measurement tools, not part of the product ``libdmnist_b200.so``."""
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    os.makedirs(LIB_DIR, exist_ok=True)
+    srcs = sorted(os.path.join(PROBE_DIR, f) for f in os.listdir(PROBE_DIR) if f.endswith(".cu"))
+    srcs.append(os.path.join(CSRC, "host_utils.cu"))
+    cmd = [NVCC] + ARCH_FLAGS + [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")] + ["-I", CSRC, "-shared", "-o", PROBE_LIB_PATH] \
+        + srcs + ["-cudart", "static", "-lrt", "-lpthread", "-ldl"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("probe build failed:\n%s" % (r.stdout + r.stderr)[-4000:])
+    return PROBE_LIB_PATH
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv)
+    if "--probes" in sys.argv:
+        print(build_probes())

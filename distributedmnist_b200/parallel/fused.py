@@ -295,6 +295,13 @@ class FusedBackend(Backend):
                                           ctypes.c_uint(int(usec)), ctypes.c_uint(seed), stream_ptr(stream)),
               "dm_straggler_delay")
 
+    def device_barrier(self, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Stream-ordered barrier over NVLink flags (csrc/fused_sync.cu): every replica's stream passes it within a flag hop of
+        the last replica reaching it -- aligns the replicas far tighter than a host-side barrier can."""
+        if self.ctx.world_size > 1:
+            check(self.lib.dm_device_barrier(self.ctrl.ptr_table(), self.ctx.rank, self.ctx.world_size,
+                                             ctypes.c_double(self.timeout_ms), stream_ptr(stream)), "dm_device_barrier")
+
     def enqueue_stamp_start(self, stream: Optional[torch.cuda.Stream] = None) -> None:
         check(self.lib.dm_stamp_start(ctypes.c_void_p(self.ctrl.local_ptr), stream_ptr(stream)), "dm_stamp_start")
 

@@ -1,5 +1,5 @@
 """Do CTAs of different kernels share an SM?  Launch a resident kernel (1 CTA/SM, spinning 60 us) and a guest kernel on
-another stream; report when the guest's CTAs started relative to the residents (csrc/coresidency_probe.cu)."""
+another stream; report when the guest's CTAs started relative to the residents (csrc/probes/coresidency_probe.cu)."""
 import ctypes
 import os
 import sys
@@ -9,7 +9,9 @@ import torch  # noqa: E402
 
 from distributedmnist_b200.ops.lib import check, load, ptr  # noqa: E402
 
-lib = load()
+from distributedmnist_b200.ops.build import build_probes  # noqa: E402
+
+lib = ctypes.CDLL(build_probes())       # the probes live in their own library (csrc/probes/)
 out = torch.zeros(5, dtype=torch.int64, device="cuda")
 sink = torch.zeros(4, device="cuda")
 lo, hi = 0, -1

@@ -1,4 +1,4 @@
-"""Hardware probe (see csrc/umma_probe.cu): UMMA descriptors starting at a row offset inside a swizzled tile."""
+"""Hardware probe (see csrc/probes/umma_probe.cu): UMMA descriptors starting at a row offset inside a swizzled tile."""
 import ctypes
 import os
 import sys
@@ -10,7 +10,9 @@ from distributedmnist_b200.ops.lib import check, load, ptr, stream_ptr  # noqa: 
 
 
 def main():
-    lib = load()
+    import ctypes
+    from distributedmnist_b200.ops.build import build_probes
+    lib = ctypes.CDLL(build_probes())       # the probes live in their own library (csrc/probes/)
     os.makedirs("gpurun_out", exist_ok=True)
     lines = []
     torch.manual_seed(0)

@@ -34,7 +34,7 @@ if has c1wg64; then
   echo "c1wg64 diag exit=$?"; sed -n '/^====/,$p' gpurun_out/diag_c1wg64.log | cut -c1-150
 fi
 if has mgtests; then
-  timeout 900 python -m pytest tests/test_fused_sync_gpu.py -m gpu -x -q > gpurun_out/pytest_multigpu.log 2>&1
+  timeout 900 python -m pytest tests/test_fused_sync_gpu.py -m gpu -x -q ${MGTESTS_K:+-k "$MGTESTS_K"} > gpurun_out/pytest_multigpu.log 2>&1
   echo "pytest(multi-gpu) exit=$?" >> gpurun_out/pytest_multigpu.log; tail -30 gpurun_out/pytest_multigpu.log | cut -c1-400
 fi
 if has tests; then
