@@ -263,8 +263,16 @@ def main():
     # at least 30 untimed steps: the first two capture the step graphs, the next ones bring the host-side launch path, the
     # copy engine and the L2-resident working set (weights, activations) to steady state; the count is reported as `warmup`
     n_warm = max(args.warmup, 30)
-    for i in range(n_warm):
-        device_step(i)
+    if k == n:
+        for i in range(n_warm):
+            device_step(i)
+    else:
+        # backup workers: replicas are not in lock step, so also the warm-up is a window of GLOBAL steps -- a fixed number of
+        # local iterations would leave the delayed replica alone at the end, waiting for arrivals that never come
+        for i in range(2):
+            device_step(i)                   # both slot graphs get captured (every replica still launches: no starvation yet)
+        barrier()
+        run_global_steps(device_step, n_warm)
     barrier()
 
     # ---- device-timed K steps ------------------------------------------------------------------------------------
@@ -293,8 +301,11 @@ def main():
     launches = engine.launches_per_step * args.steps
 
     # ---- end-to-end K steps (public API: pinned H2D every step, loss D2H every step) --------------------------------
-    for i in range(3):
-        e2e_step(i)[0].synchronize()
+    if k == n:
+        for i in range(3):
+            e2e_step(i)[0].synchronize()
+    else:
+        run_global_steps(lambda i: e2e_step(i)[0].synchronize(), 3)
     barrier()
     backend.device_barrier()
     e0.record()

@@ -376,19 +376,41 @@ __global__ void __launch_bounds__(LATE2_THREADS) bucket_late_ll_kernel(SyncPeers
     const int i = (j < r.fc1_b4) ? j : j + early_n4;
     const float4 own = *reinterpret_cast<const float4*>(g_local + 4 * (size_t)i);
     float4 g[SYNC_MAX_RANKS];
+    // all N-1 slots are polled TOGETHER: the loads of every replica's lines are in flight at once (a line that has just
+    // landed from NVLink costs a full memory latency; polling the slots one after the other serialised 7 of those at N = 8)
+    const uint4* src = inbox + half + 2 * (size_t)j;
+    uint32_t pending = ((NR >= 32) ? 0xffffffffu : ((1u << NR) - 1u)) & ~(1u << a.rank);
 #pragma unroll
-    for (int c = 0; c < SYNC_MAX_RANKS; ++c) {
-      if (c >= NR) continue;
-      if (c == a.rank) { g[c] = own; continue; }
-      const uint4* src = inbox + half + (size_t)c * lines_per_slot + 2 * (size_t)j;
-      uint4 l0, l1;
-      const bool ok = spin_until([&] {
-        l0 = ld_volatile_b128(src);
-        l1 = ld_volatile_b128(src + 1);
-        return l0.y == tag && l0.w == tag && l1.y == tag && l1.w == tag;
-      }, a.timeout_ns);
-      if (!ok) me->error = 1;
-      g[c] = make_float4(__uint_as_float(l0.x), __uint_as_float(l0.z), __uint_as_float(l1.x), __uint_as_float(l1.z));
+    for (int c = 0; c < SYNC_MAX_RANKS; ++c)
+      if (c == a.rank) g[c] = own;                  // (compile-time indices: g[] stays in registers)
+    unsigned long long t0 = 0;
+    unsigned spins = 0;
+    while (pending) {
+      uint4 l0[SYNC_MAX_RANKS], l1[SYNC_MAX_RANKS];
+#pragma unroll
+      for (int c = 0; c < SYNC_MAX_RANKS; ++c) {
+        if ((pending >> c) & 1u) {
+          l0[c] = ld_volatile_b128(src + (size_t)c * lines_per_slot);
+          l1[c] = ld_volatile_b128(src + (size_t)c * lines_per_slot + 1);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < SYNC_MAX_RANKS; ++c) {
+        if (((pending >> c) & 1u) && l0[c].y == tag && l0[c].w == tag && l1[c].y == tag && l1[c].w == tag) {
+          g[c] = make_float4(__uint_as_float(l0[c].x), __uint_as_float(l0[c].z), __uint_as_float(l1[c].x), __uint_as_float(l1[c].z));
+          pending &= ~(1u << c);
+        }
+      }
+      if (pending && ++spins > 64) {            // busy-poll first, then back off; watchdog instead of a hang
+        if (t0 == 0) t0 = globaltimer_ns();
+        __nanosleep(64);
+        if ((spins & 255) == 0 && globaltimer_ns() - t0 > a.timeout_ns) { me->error = 1; break; }
+      }
+    }
+    if (pending) {
+#pragma unroll
+      for (int c = 0; c < SYNC_MAX_RANKS; ++c)
+        if ((pending >> c) & 1u) g[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float4 nw = *reinterpret_cast<const float4*>(wdst + 4 * (size_t)i);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -483,7 +505,9 @@ int dm_bucket_sync(void* const* ctrl, void* const* params, void* const* grads, v
   const int n_late4 = r.numel4 - (r.fc1_e4 - r.fc1_b4);
   int grid = (n_late4 + LATE2_THREADS - 1) / LATE2_THREADS;      // one float4 per thread: a single round of loads
   if (grid < 1) grid = 1;
-  if (late_ll) {                                                  // no in-kernel barrier: any grid size is safe
+  // LL lines double the bytes and poll per element: the right protocol for a latency-bound SMALL bucket (LeNet: 236 KB); a
+  // large late bucket (the MLPs: megabytes) is bandwidth-bound and goes as plain data + release flags
+  if (late_ll && (long long)n_late4 * 16 <= (1ll << 20)) {        // no in-kernel barrier: any grid size is safe
     if (grid > 296) grid = 296;
     return (int)launch_kernel(bucket_late_ll_kernel, dim3(grid), dim3(LATE2_THREADS), 0, stream, P, a, r);
   }

@@ -320,7 +320,7 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& tmA, const CU
 // D[M,N] = A * B with bf16 operands.
 //   a_mn == 0: A is [M rows][K cols] (lda elements between rows);   a_mn == 1: A is [K rows][M cols].
 //   b_mn == 0: B is [N rows][K cols] (ldb);                          b_mn == 1: B is [K rows][N cols].
-//   epi: 0 store fp32, 1 atomicAdd fp32 (split-K; caller zeroes), 2 store bf16.   bn: 64 or 128.
+//   epi: 0 store fp32, 1 atomicAdd fp32 (split-K; caller zeroes), 2 store bf16, 3 bias+ReLU -> bf16.   bn: 64, 128 or 256.
 //   split-K without atomics: epi 0 with splits > 1 and split_stride > 0 -> partial sums at out + z*split_stride
 //   (the consumer adds the `splits` partials while loading).
 extern "C" int dm_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, int lda, int ldb, int ldo,
@@ -328,7 +328,7 @@ extern "C" int dm_gemm_bf16(const void* A, const void* B, void* out, int M, int 
                             void* stream_) {
   using namespace dm;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if ((bn != 64 && bn != 128) || epi < 0 || epi > 3 || splits < 1) return -1;
+  if ((bn != 64 && bn != 128 && bn != 256) || epi < 0 || epi > 3 || splits < 1) return -1;
   if (epi == EPI_BIAS_RELU_BF16 && bias == nullptr) return -4;
   if (splits > 1 && !(epi == EPI_ATOMIC_F32 || (epi == EPI_STORE_F32 && split_stride > 0))) return -2;
   if ((lda & 7) || (ldb & 7)) return -3;   // TMA: global strides are multiples of 16 bytes
@@ -349,11 +349,18 @@ extern "C" int dm_gemm_bf16(const void* A, const void* B, void* out, int M, int 
     if (epi == 1) DM_DISPATCH(64, 1);
     if (epi == 2) DM_DISPATCH(64, 2);
     DM_DISPATCH(64, 3);
-  } else {
+  } else if (bn == 128) {
     if (epi == 0) DM_DISPATCH(128, 0);
     if (epi == 1) DM_DISPATCH(128, 1);
     if (epi == 2) DM_DISPATCH(128, 2);
     DM_DISPATCH(128, 3);
+  } else {
+    // 128 x 256 tiles: twice the FLOPs per operand byte fetched from L2 (the large MLP GEMMs are L2->SM bandwidth bound with
+    // 128 x 128 tiles: 2048 CTAs x 2 MB of operands each), M128 N256 K16 instructions run at the tensor-pipe floor
+    if (epi == 0) DM_DISPATCH(256, 0);
+    if (epi == 2) DM_DISPATCH(256, 2);
+    if (epi == 3) DM_DISPATCH(256, 3);
+    return -1;
   }
 #undef DM_DISPATCH
 }

@@ -613,6 +613,8 @@ class CudaMlpEngine(ComputeEngine):
         self.model, self.batch_size, self.hidden = model, batch_size, hidden
         self.n_layers = len(self.spec.params) // 2
         self.use_graph = use_graph
+        # 128 x 256 GEMM tiles when the hidden width allows: half the L2->SM operand traffic per FLOP of 128 x 128
+        self._bn = 256 if (hidden % 256 == 0 and os.environ.get("DMNIST_GEMM_BN256", "1") != "0") else 128
         B, dev, bf = batch_size, self.device, torch.bfloat16
         self.params = backend.allocate(self.spec.arena_numel)
         self.params.copy_(self.spec.init_flat(seed).to(dev))
@@ -691,7 +693,7 @@ class CudaMlpEngine(ComputeEngine):
         for i in range(1, self.n_layers):
             # h_i = relu(src @ W_i + b_i): A K-major, B = W_i [in,out] MN-major, bias+ReLU in the epilogue
             G.gemm_bf16_raw(src, pb["fc%d_weights" % i], self.h[i - 1], B, H, K, K, H, H, False, True,
-                            G.EPI_BIAS_RELU_BF16, bn=128, bias=p["fc%d_biases" % i])
+                            G.EPI_BIAS_RELU_BF16, bn=self._bn, bias=p["fc%d_biases" % i])
             src, K = self.h[i - 1], H
             n += 1
         L = self.n_layers
@@ -720,7 +722,7 @@ class CudaMlpEngine(ComputeEngine):
             early = early_sync and self._early_name == "fc%d_weights" % i
             # dW_i[in,H] = src^T (MN-major) * dh_i (MN-major), K = batch
             if early:
-                G.gemm_bf16_raw(src, self.dh[i - 1], self._g16_view, K, H, B, K, H, H, True, True, G.EPI_STORE_BF16, bn=128)
+                G.gemm_bf16_raw(src, self.dh[i - 1], self._g16_view, K, H, B, K, H, H, True, True, G.EPI_STORE_BF16, bn=self._bn)
                 e0, e1 = self._bucket_early
                 ev = torch.cuda.Event()
                 ev.record(main)
@@ -734,12 +736,12 @@ class CudaMlpEngine(ComputeEngine):
                     self._join_early.record(side)
             else:
                 G.gemm_bf16_raw(src, self.dh[i - 1], g["fc%d_weights" % i], K, H, B, K, H, H, True, True,
-                                G.EPI_STORE_F32, bn=128)
+                                G.EPI_STORE_F32, bn=self._bn)
             n += 1
             if i > 1:
                 # dh_{i-1} = (dh_i @ W_i^T) * relu'(h_{i-1});  W_i [in,out]: rows = in (N), K = out contiguous
                 G.gemm_bf16_raw(self.dh[i - 1], pb["fc%d_weights" % i], self.dh[i - 2], B, H, H, H, H, H, False, False,
-                                G.EPI_STORE_BF16, bn=128)
+                                G.EPI_STORE_BF16, bn=self._bn)
                 if early:
                     # the data-gradient GEMM above was the last reader of this layer's bf16 shadow: the apply may rewrite it
                     ev2 = torch.cuda.Event()

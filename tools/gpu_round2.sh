@@ -89,7 +89,7 @@ PY
 fi
 if has kofn; then
   K=$((GPUS-2)); [ "$K" -lt 1 ] && K=1
-  DMNIST_BENCH_ABORT_S=60 run_bench --k $K --straggler $((GPUS-1)):1.0:300 --steps 200 --warmup 10 > gpurun_out/bench_kofn_$GPUS.json 2> gpurun_out/bench_kofn_$GPUS.err
+  DMNIST_DEBUG_SYNC=1 DMNIST_BENCH_ABORT_S=60 run_bench --k $K --straggler $((GPUS-1)):1.0:300 --steps 200 --warmup 10 > gpurun_out/bench_kofn_$GPUS.json 2> gpurun_out/bench_kofn_$GPUS.err
   echo "bench K=$K of $GPUS (rank $((GPUS-1)) delayed 300 us/step) exit=$?"; cat gpurun_out/bench_kofn_$GPUS.json; tail -5 gpurun_out/bench_kofn_$GPUS.err
 fi
 if has mlp3; then
@@ -103,10 +103,36 @@ if has sweep; then
   done
 fi
 if has cdf; then
-  rm -rf /tmp/cdf_train
-  run_py 300 src/mnist_distributed_train.py --job_name=worker --batch_size=256 --max_steps=520 --log_every=50 \
-      --worker_times_cdf_method=true --inject_straggler=$((GPUS-1)):0.3:300 --train_dir=/tmp/cdf_train --save_interval_secs=1000 > gpurun_out/cdf_$GPUS.log 2>&1
-  echo "cdf exit=$?"; grep -c "ELAPSED TIMES" gpurun_out/cdf_$GPUS.log
-  mkdir -p gpurun_out/cdf_$GPUS; cp /tmp/cdf_train/../cdf_train/out_* gpurun_out/cdf_$GPUS/ 2>/dev/null
+  # cdf mode (full barrier + per-iteration timing) with a device-side straggler on the last rank: the ELAPSED TIMES tables come
+  # from the %globaltimer stamps of the step's kernels, so only the delayed rank shows a tail
+  rm -rf /tmp/cdf_train; mkdir -p gpurun_out/cdf_$GPUS
+  run_py 300 src/mnist_distributed_train.py --job_name=worker --batch_size=256 --max_steps=520 --log_every=100 \
+      --worker_times_cdf_method=true --inject_straggler=$((GPUS-1)):0.3:300 --train_dir=/tmp/cdf_train --save_interval_secs=1000 \
+      > gpurun_out/cdf_$GPUS/b256_straggler_${GPUS}gpu_out_master 2>&1
+  echo "cdf exit=$?"; grep -c "ELAPSED TIMES" gpurun_out/cdf_$GPUS/b256_straggler_${GPUS}gpu_out_master
+  python - <<PY
+import sys
+sys.path.insert(0, "tools")
+import benchmark as B
+d = "gpurun_out/cdf_$GPUS"
+print(B.plot_time_cdfs(d, d))
+import collections
+ct = B.extract_compute_times(d + "/b256_straggler_${GPUS}gpu_out_master")
+per = collections.defaultdict(list)
+for t, w, it in ct:
+    per[w].append(t)
+for w in sorted(per):
+    v = sorted(per[w]); n = len(v)
+    print("worker %d: n=%d median=%.1f us p95=%.1f us max=%.1f us" % (w, n, v[n // 2] * 1e6, v[int(n * 0.95)] * 1e6, v[-1] * 1e6))
+PY
+fi
+if has matrix; then
+  # the reference's experiment matrices on this box: K-of-N sweep + interval sweep (time-to-accuracy, step rate, loss) and the
+  # compute-time CDF study; figures + scraped logs land in gpurun_out/matrix_*
+  for m in ${MATRIX:-8_gpus time_cdf_cfgs}; do
+    timeout ${MATRIX_TIMEOUT:-600} python tools/benchmark.py use_dir cfg/$m --n_iters=${MATRIX_ITERS:-19000} \
+        --outdir=gpurun_out/matrix_$m --dest=gpurun_out/matrix_$m > gpurun_out/matrix_$m.log 2>&1
+    echo "matrix $m exit=$?"; tail -25 gpurun_out/matrix_$m.log | cut -c1-200; ls gpurun_out/matrix_$m | head -40
+  done
 fi
 ls gpurun_out | head -50
