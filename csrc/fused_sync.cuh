@@ -106,6 +106,20 @@ DMNIST_DEVICE unsigned long long ld_acquire_sys64(const volatile unsigned long l
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+// Polling loads: RELAXED (an acquire load costs a CCTL.IVALL -- it invalidates the SM's whole L1 -- on EVERY poll, which is
+// poison for the tensor-core kernels the small aggregation CTAs are co-resident with); the one acquire fence a wait needs is
+// issued by spin_until() when the wait is over.
+DMNIST_DEVICE uint32_t ld_relaxed_sys(const volatile uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+DMNIST_DEVICE unsigned long long ld_relaxed_sys64(const volatile unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+DMNIST_DEVICE void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 DMNIST_DEVICE void st_release_sys(volatile uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -163,19 +177,22 @@ DMNIST_DEVICE float device_lr(const SyncArgs& a, uint32_t step) {
   return a.lr0 * __powf(a.decay_rate, p);
 }
 
-// Poll until pred() or the watchdog fires.
+// Poll (relaxed loads inside pred) until pred() or the watchdog fires; ONE acquire fence when the wait is over.
 template <class Pred>
 DMNIST_DEVICE bool spin_until(Pred pred, unsigned long long timeout_ns) {
-  if (pred()) return true;
-  const unsigned long long t0 = globaltimer_ns();
-  unsigned spins = 0;
-  while (!pred()) {
-    if (++spins > 64) {          // busy-poll first (the common wait is a few microseconds), then back off
-      __nanosleep(64);
-      if ((spins & 255) == 0 && globaltimer_ns() - t0 > timeout_ns) return false;
+  bool ok = true;
+  if (!pred()) {
+    const unsigned long long t0 = globaltimer_ns();
+    unsigned spins = 0;
+    while (!pred()) {
+      if (++spins > 64) {          // busy-poll first (the common wait is a few microseconds), then back off
+        __nanosleep(64);
+        if ((spins & 255) == 0 && globaltimer_ns() - t0 > timeout_ns) { ok = false; break; }
+      }
     }
   }
-  return true;
+  fence_acq_rel_sys();
+  return ok;
 }
 
 }  // namespace dm

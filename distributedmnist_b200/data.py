@@ -117,13 +117,19 @@ class DataSet:
         self._labels = labels
         self._epochs_completed = 0
         self._index_in_epoch = 0
+        self._perm = np.arange(self._num_examples)
         if not fake_data:
-            self._shuffle()
+            # the initial shuffle re-orders the arrays themselves (one copy at start-up; `images` / `labels` then expose a
+            # per-replica order, as in the reference); the per-epoch reshuffles only draw a new permutation
+            perm = self._rng.permutation(self._num_examples)
+            self._images = self._images[perm]
+            self._labels = self._labels[perm]
 
     def _shuffle(self) -> None:
-        perm = self._rng.permutation(self._num_examples)
-        self._images = self._images[perm]
-        self._labels = self._labels[perm]
+        # A fresh permutation per epoch, applied when a batch is drawn (row gather of `batch_size` examples) instead of
+        # re-ordering the whole arrays: at B200 speed an epoch of 60 000 images lasts ~20 ms, and copying 188 MB per epoch
+        # cost more than the training it fed.
+        self._perm = self._rng.permutation(self._num_examples)
 
     @property
     def images(self):
@@ -159,7 +165,21 @@ class DataSet:
             start = 0
             self._index_in_epoch = batch_size
         end = self._index_in_epoch
-        return self._images[start:end], self._labels[start:end]
+        idx = self._perm[start:end]
+        return self._images[idx], self._labels[idx]
+
+    def next_batch_indices(self, batch_size: int) -> np.ndarray:
+        """The row indices ``next_batch`` would use (same epoch / reshuffle bookkeeping), for input pipelines that gather
+        straight into their own (page-locked) buffers."""
+        assert not self.fake_data and batch_size <= self._num_examples
+        start = self._index_in_epoch
+        self._index_in_epoch += batch_size
+        if self._index_in_epoch > self._num_examples:
+            self._epochs_completed += 1
+            self._shuffle()
+            start = 0
+            self._index_in_epoch = batch_size
+        return self._perm[start:self._index_in_epoch]
 
 
 # ----------------------------------------------------------------------------

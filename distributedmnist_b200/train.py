@@ -83,24 +83,45 @@ class _BatchPacker:
     input is ONE host->device DMA and the hot loop never touches numpy.  Buffers rotate through a ring deep enough that a
     buffer is not rewritten before the copy that reads it has run (the engine double-buffers its device slots)."""
 
-    def __init__(self, engine, dataset, batch_size: int, depth: int = 6):
+    def __init__(self, engine, dataset, batch_size: int, depth: int = 8, workers: int = 2):
         import queue
         self.engine, self.dataset, self.batch_size = engine, dataset, batch_size
         B = batch_size
         self._nimg = B * 784 * 4
-        self.ring = [torch.empty(B * 784 * 4 + B * 8, dtype=torch.uint8).pin_memory() for _ in range(depth + 3)]
+        self.workers = max(1, workers)
+        # every worker owns a private ring segment deep enough that a buffer is never rewritten while the DMA that reads it
+        # may still be pending (the queue bounds how far ahead of the training loop the workers can run)
+        self.rings = [[torch.empty(B * 784 * 4 + B * 8, dtype=torch.uint8).pin_memory() for _ in range(depth + 4)]
+                      for _ in range(self.workers)]
         self.ready: "queue.Queue" = queue.Queue(maxsize=depth)
+        self._draw = threading.Lock()          # batches are drawn from the DataSet one at a time; the gathers run in parallel
         self._stop = False
-        self._thread = threading.Thread(target=self._run, daemon=True)
-        self._thread.start()
+        # fast path: gather the batch's rows straight from the dataset arrays into the page-locked buffer with torch
+        # (multi-threaded, releases the GIL -- the training loop's interpreter is not held up by the packer)
+        self._src = None
+        if hasattr(dataset, "next_batch_indices") and not getattr(dataset, "fake_data", False):
+            imgs = np.ascontiguousarray(dataset.images, dtype=np.float32).reshape(dataset.num_examples, -1)
+            if imgs.shape[1] == 784:
+                self._src = (torch.from_numpy(imgs), torch.from_numpy(np.ascontiguousarray(dataset.labels)).to(torch.int64))
+        self._threads = [threading.Thread(target=self._run, args=(w,), daemon=True) for w in range(self.workers)]
+        for t in self._threads:
+            t.start()
 
-    def _run(self) -> None:
+    def _run(self, w: int) -> None:
         i = 0
+        ring = self.rings[w]
         while not self._stop:
-            buf = self.ring[i % len(self.ring)]
-            images, labels = self.dataset.next_batch(self.batch_size)
-            buf[:self._nimg].view(torch.float32).copy_(torch.from_numpy(np.ascontiguousarray(images, dtype=np.float32)).reshape(-1))
-            buf[self._nimg:].view(torch.int64).copy_(torch.from_numpy(np.ascontiguousarray(labels)).to(torch.int64).reshape(-1))
+            buf = ring[i % len(ring)]
+            if self._src is not None:
+                with self._draw:
+                    idx = torch.from_numpy(self.dataset.next_batch_indices(self.batch_size).copy())
+                torch.index_select(self._src[0], 0, idx, out=buf[:self._nimg].view(torch.float32).view(self.batch_size, 784))
+                torch.index_select(self._src[1], 0, idx, out=buf[self._nimg:].view(torch.int64))
+            else:
+                with self._draw:
+                    images, labels = self.dataset.next_batch(self.batch_size)
+                buf[:self._nimg].view(torch.float32).copy_(torch.from_numpy(np.ascontiguousarray(images, dtype=np.float32)).reshape(-1))
+                buf[self._nimg:].view(torch.int64).copy_(torch.from_numpy(np.ascontiguousarray(labels)).to(torch.int64).reshape(-1))
             while not self._stop:
                 try:
                     self.ready.put(buf, timeout=0.1)
@@ -119,7 +140,8 @@ class _BatchPacker:
                 self.ready.get_nowait()
         except Exception:  # noqa: BLE001  (queue.Empty)
             pass
-        self._thread.join(timeout=2.0)
+        for t in self._threads:
+            t.join(timeout=2.0)
 
 
 def train(ctx: ReplicaContext, dataset, dataset_test=None, flags=FLAGS) -> Dict:
