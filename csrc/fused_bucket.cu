@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(EARLY2_THREADS) bucket_early_kernel(SyncPeers 
     // ---- every rank's fc1_wgrad is complete (all-to-all flags: CTA 0 tells the peers, everybody watches the local words) ----
     if (threadIdx.x < NR) {
       if (blockIdx.x == 0) st_release_sys(&P.ctrl[threadIdx.x]->arrive_e[a.rank * 32], epoch + 1);
-      const bool ok = spin_until([&] { return ld_relaxed_sys(&me->arrive_e[threadIdx.x * 32]) >= epoch + 1; }, a.timeout_ns);
+      const bool ok = spin_until([&] { return ld_relaxed_sys(&me->arrive_e[threadIdx.x * 32]) >= epoch + 1; }, a.timeout_ns, &me->arrive_e[threadIdx.x * 32]);
       if (!ok) me->error = 1;
     }
     __syncthreads();
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(EARLY2_THREADS) bucket_early_kernel(SyncPeers 
   if (!(parts & 2)) return;
   if (NR > 1) {
     if (threadIdx.x < NR) {
-      const bool ok = spin_until([&] { return ld_relaxed_sys(&me->done_e[threadIdx.x * 32]) >= epoch + 1; }, a.timeout_ns);
+      const bool ok = spin_until([&] { return ld_relaxed_sys(&me->done_e[threadIdx.x * 32]) >= epoch + 1; }, a.timeout_ns, &me->done_e[threadIdx.x * 32]);
       if (!ok) me->error = 2;
     }
     __syncthreads();
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(LATE2_THREADS, 1) bucket_late_kernel(SyncPeers
     }
     // ---- every replica's push has landed in MY inbox? ------------------------------------------------------------------------
     if (threadIdx.x < NR) {
-      const bool ok = spin_until([&] { return ld_relaxed_sys(&me->arrive[threadIdx.x * 32]) >= epoch + 1; }, a.timeout_ns);
+      const bool ok = spin_until([&] { return ld_relaxed_sys(&me->arrive[threadIdx.x * 32]) >= epoch + 1; }, a.timeout_ns, &me->arrive[threadIdx.x * 32]);
       if (!ok) me->error = 1;
     }
     __syncthreads();

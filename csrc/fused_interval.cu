@@ -142,7 +142,7 @@ DMNIST_DEVICE void iv_close(const SyncPeers& P, const SyncArgs& a, SyncCtrl* me)
   for (int q = 0; q < a.nranks; ++q) {
     if (!((mask >> q) & 1u)) continue;
     if (q != a.rank) {
-      const bool ok = spin_until([&] { return ld_relaxed_sys(&P.ctrl[q]->iv_busy) != e + 1; }, a.timeout_ns);
+      const bool ok = spin_until([&] { return ld_relaxed_sys(&P.ctrl[q]->iv_busy) != e + 1; }, a.timeout_ns, &P.ctrl[q]->iv_busy);
       if (!ok) me->error = 1;
     }
     const unsigned long long sq = q == a.rank ? st : ld_acquire_sys64(&P.ctrl[q]->iv_state);

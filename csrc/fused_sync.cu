@@ -45,7 +45,7 @@ DMNIST_DEVICE void decide(const SyncPeers& P, const SyncArgs& a, SyncCtrl* me, u
     if (lane < a.nranks) st_release_sys(&P.ctrl[lane]->arrive[a.rank * 32], epoch + 1);
     bool ok = true;
     if (lane < a.nranks)
-      ok = spin_until([&] { return ld_relaxed_sys(&me->arrive[lane * 32]) >= epoch + 1; }, a.timeout_ns);
+      ok = spin_until([&] { return ld_relaxed_sys(&me->arrive[lane * 32]) >= epoch + 1; }, a.timeout_ns, &me->arrive[lane * 32]);
     if (!__all_sync(0xffffffffu, ok) && lane == 0) me->error = 1;
   } else {
     SyncCtrl* chief = P.ctrl[0];
@@ -77,7 +77,8 @@ DMNIST_DEVICE void decide(const SyncPeers& P, const SyncArgs& a, SyncCtrl* me, u
         }
         // wait for the commit word of my step to reach my control block
         const bool ok = spin_until(
-            [&] { cw = ld_relaxed_sys64(&me->commit_local[slot]); return (cw >> 32) >= want_tag; }, a.timeout_ns);
+            [&] { cw = ld_relaxed_sys64(&me->commit_local[slot]); return (cw >> 32) >= want_tag; }, a.timeout_ns,
+            reinterpret_cast<const volatile uint32_t*>(&me->commit_local[slot]));
         if (!ok) me->error = 1;
       }
       if ((cw >> 32) == want_tag) {
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_sgd_kernel(SyncPee
       if (won) decide<KOFN>(P, a, me, epoch);
     }
     if (threadIdx.x == 0) {
-      spin_until([&] { return ld_relaxed_sys(&me->decided_tag) == epoch + 1; }, a.timeout_ns * 2);
+      spin_until([&] { return ld_relaxed_sys(&me->decided_tag) == epoch + 1; }, a.timeout_ns * 2, &me->decided_tag);
       s_mask = me->decided_mask;
       s_late = me->decided_late;
       s_target = me->decided_target;
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_sgd_kernel(SyncPee
     const int q = threadIdx.x;
     uint32_t need = ((mask >> q) & 1u) ? epoch + 1 : 0u;
     if (KOFN && late) need = ld_acquire_sys(&P.ctrl[0]->last_in_mask[q]);   // fast-forward: everything committed so far
-    const bool ok = spin_until([&] { return ld_relaxed_sys(&me->done[q * 32]) >= need; }, a.timeout_ns);
+    const bool ok = spin_until([&] { return ld_relaxed_sys(&me->done[q * 32]) >= need; }, a.timeout_ns, &me->done[q * 32]);
     if (!ok) me->error = 2;
   }
   __syncthreads();
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(EARLY_THREADS) fused_sync_early_kernel(SyncPee
   // arrival: CTA 0 tells every peer, every CTA watches the local flags (local polls are free)
   if (threadIdx.x < a.nranks) {
     if (blockIdx.x == 0) st_release_sys(&P.ctrl[threadIdx.x]->arrive_e[a.rank * 32], epoch + 1);
-    const bool ok = spin_until([&] { return ld_relaxed_sys(&me->arrive_e[threadIdx.x * 32]) >= epoch + 1; }, a.timeout_ns);
+    const bool ok = spin_until([&] { return ld_relaxed_sys(&me->arrive_e[threadIdx.x * 32]) >= epoch + 1; }, a.timeout_ns, &me->arrive_e[threadIdx.x * 32]);
     if (!ok) me->error = 1;
   }
   __syncthreads();
@@ -428,7 +429,7 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_late_kernel(SyncPe
   }
   if (threadIdx.x < a.nranks) {
     if (blockIdx.x == 0) st_release_sys(&P.ctrl[threadIdx.x]->arrive[a.rank * 32], epoch + 1);
-    const bool ok = spin_until([&] { return ld_relaxed_sys(&me->arrive[threadIdx.x * 32]) >= epoch + 1; }, a.timeout_ns);
+    const bool ok = spin_until([&] { return ld_relaxed_sys(&me->arrive[threadIdx.x * 32]) >= epoch + 1; }, a.timeout_ns, &me->arrive[threadIdx.x * 32]);
     if (!ok) me->error = 1;
   }
   __syncthreads();
@@ -472,7 +473,7 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_late_kernel(SyncPe
 
   // ---- the early bucket's pushes (sent while the backward pass was still running) have landed in my arena? -------------------
   if (threadIdx.x < a.nranks) {
-    const bool ok = spin_until([&] { return ld_relaxed_sys(&me->done_e[threadIdx.x * 32]) >= epoch + 1; }, a.timeout_ns);
+    const bool ok = spin_until([&] { return ld_relaxed_sys(&me->done_e[threadIdx.x * 32]) >= epoch + 1; }, a.timeout_ns, &me->done_e[threadIdx.x * 32]);
     if (!ok) me->error = 2;
   }
   __syncthreads();
@@ -494,7 +495,7 @@ __global__ void __launch_bounds__(SYNC_THREADS, 1) fused_sync_late_kernel(SyncPe
   // ---- last CTA: nobody may still be reading MY gradient arena when the next step starts overwriting it ------------------------
   if (s_last) {
     if (threadIdx.x < a.nranks) {
-      const bool ok = spin_until([&] { return ld_relaxed_sys(&me->done[threadIdx.x * 32]) >= epoch + 1; }, a.timeout_ns);
+      const bool ok = spin_until([&] { return ld_relaxed_sys(&me->done[threadIdx.x * 32]) >= epoch + 1; }, a.timeout_ns, &me->done[threadIdx.x * 32]);
       if (!ok) me->error = 2;
     }
     __syncthreads();
@@ -539,7 +540,7 @@ __global__ void device_barrier_kernel(SyncPeers P, int rank, int nranks, unsigne
   const uint32_t seq = me->bar_seq + 1;
   if (threadIdx.x < nranks) {
     st_release_sys(&P.ctrl[threadIdx.x]->bar[rank * 32], seq);
-    if (!spin_until([&] { return ld_relaxed_sys(&me->bar[threadIdx.x * 32]) >= seq; }, timeout_ns)) me->error = 1;
+    if (!spin_until([&] { return ld_relaxed_sys(&me->bar[threadIdx.x * 32]) >= seq; }, timeout_ns, &me->bar[threadIdx.x * 32])) me->error = 1;
   }
   __syncthreads();
   if (threadIdx.x == 0) me->bar_seq = seq;

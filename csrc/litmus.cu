@@ -39,12 +39,12 @@ __global__ void __launch_bounds__(256, 1) litmus_mp_kernel(LitmusArgs a) {
       if (threadIdx.x == 0) {
         __threadfence_system();
         st_release_sys(a.flag_peer, (uint32_t)round);
-        if (!spin_until([&] { return ld_relaxed_sys(a.flag_local + 32) >= (uint32_t)round; }, a.timeout_ns)) s_abort = 1;
+        if (!spin_until([&] { return ld_relaxed_sys(a.flag_local + 32) >= (uint32_t)round; }, a.timeout_ns, a.flag_local + 32)) s_abort = 1;
       }
       __syncthreads();
     } else {
       if (threadIdx.x == 0)
-        if (!spin_until([&] { return ld_relaxed_sys(a.flag_local) >= (uint32_t)round; }, a.timeout_ns)) s_abort = 1;
+        if (!spin_until([&] { return ld_relaxed_sys(a.flag_local) >= (uint32_t)round; }, a.timeout_ns, a.flag_local)) s_abort = 1;
       __syncthreads();
       if (!s_abort) {
         for (int i = threadIdx.x; i < a.n; i += blockDim.x) {

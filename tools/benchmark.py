@@ -43,6 +43,14 @@ def load_cfg_from_file(cfg_file: str) -> Cfg:
     from cluster import cfg as default_cfg
     merged = dict(default_cfg)          # raw (un-interpolated) defaults, then the file's overrides
     merged.update(ast.literal_eval(call.args[0]))
+    if os.environ.get("DMNIST_CLAMP_GPUS", "0") == "1" and merged.get("n_gpus"):
+        # dry runs of an 8-GPU matrix on a smaller box: as many replicas as there are GPUs, K clamped accordingly
+        from cluster import n_gpus_available
+        have = n_gpus_available()
+        if have and merged["n_masters"] + merged["n_workers"] > have:
+            merged["n_workers"] = max(have - merged["n_masters"], 0)
+            k = int(merged.get("num_replicas_to_aggregate", have))
+            merged["num_replicas_to_aggregate"] = str(min(k, have))
     return Cfg(merged)
 
 

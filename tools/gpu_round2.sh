@@ -126,13 +126,33 @@ for w in sorted(per):
     print("worker %d: n=%d median=%.1f us p95=%.1f us max=%.1f us" % (w, n, v[n // 2] * 1e6, v[int(n * 0.95)] * 1e6, v[-1] * 1e6))
 PY
 fi
+if has ncu; then
+  # one full-set capture of every kernel of the (eager, un-graphed) step on ONE GPU; read here with tools/ncu_summary.py
+  timeout 900 ncu --set full --clock-control none --import-source on \
+      -k regex:'conv1_|conv2_|gemm_tc|fc2_|bucket_' -s 60 -c 36 \
+      -f -o gpurun_out/lenet_step_r2 python bench.py --steps 3 --warmup 3 --no-graph > gpurun_out/ncu_full_run.log 2>&1
+  echo "ncu full exit=$?"; ls -la gpurun_out/*.ncu-rep
+fi
+if has sanitize; then
+  for tool in memcheck racecheck; do
+    timeout 400 compute-sanitizer --tool $tool --print-limit 20 python tools/gpu_diag_lenet.py ${SAN:-conv1 fc2_loss fc1_dgrad conv2_fwd bucketed_step} \
+        > gpurun_out/sanitizer_$tool.log 2>&1
+    echo "compute-sanitizer $tool exit=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|Error|hazard" gpurun_out/sanitizer_$tool.log | head -8
+  done
+fi
 if has matrix; then
   # the reference's experiment matrices on this box: K-of-N sweep + interval sweep (time-to-accuracy, step rate, loss) and the
   # compute-time CDF study; figures + scraped logs land in gpurun_out/matrix_*
   for m in ${MATRIX:-8_gpus time_cdf_cfgs}; do
-    timeout ${MATRIX_TIMEOUT:-600} python tools/benchmark.py use_dir cfg/$m --n_iters=${MATRIX_ITERS:-19000} \
+    files=""
+    for f in $(ls cfg/$m); do
+      # MATRIX_SKIP: space-separated substrings of configuration names to leave out (budget)
+      skip=0; for pat in ${MATRIX_SKIP:-}; do [[ "$f" == *"$pat"* ]] && skip=1; done
+      [ "$skip" = 0 ] && files="$files cfg/$m/$f"
+    done
+    timeout ${MATRIX_TIMEOUT:-600} python tools/benchmark.py select_files $files --n_iters=${MATRIX_ITERS:-19000} \
         --outdir=gpurun_out/matrix_$m --dest=gpurun_out/matrix_$m > gpurun_out/matrix_$m.log 2>&1
-    echo "matrix $m exit=$?"; tail -25 gpurun_out/matrix_$m.log | cut -c1-200; ls gpurun_out/matrix_$m | head -40
+    echo "matrix $m exit=$?"; grep -E "Currently on iteration|timeout waiting|Traceback|Error" gpurun_out/matrix_$m.log | head -40; ls gpurun_out/matrix_$m | head -60
   done
 fi
 ls gpurun_out | head -50
