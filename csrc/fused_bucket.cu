@@ -322,6 +322,10 @@ DMNIST_DEVICE uint4 ld_volatile_b128(const void* p) {
   return v;
 }
 
+// BF16 = true (default): a line carries FOUR gradients as bf16 -- {bf16x2, tag, bf16x2, tag} -- i.e. one line per float4, half the
+// bytes: at N = 8 every GPU ingests 7 slots, and 7 x 475 KB of fp32 lines were ~4 us of pure NVLink ingress on the critical path.
+// Every replica sums the SAME bf16-rounded contributions (its own included) in fp32, so the replicas stay bit-identical.
+template <bool BF16>
 __global__ void __launch_bounds__(LATE2_THREADS) bucket_late_ll_kernel(SyncPeers P, SyncArgs a, BucketV2 r) {
   SyncCtrl* me = P.ctrl[a.rank];
   pdl_wait();
@@ -339,7 +343,8 @@ __global__ void __launch_bounds__(LATE2_THREADS) bucket_late_ll_kernel(SyncPeers
     me->t_phase[0] = now;
   }
   // line index space of an inbox: [2 parities][NR slots][2 * n_late4 lines of 16 bytes]
-  const size_t lines_per_slot = 2 * (size_t)n_late4;
+  constexpr int LPE = BF16 ? 1 : 2;                  // lines per float4
+  const size_t lines_per_slot = LPE * (size_t)n_late4;
   const size_t half = (size_t)(epoch & 1u) * (size_t)NR * lines_per_slot;
 
   if (NR > 1) {
@@ -347,17 +352,18 @@ __global__ void __launch_bounds__(LATE2_THREADS) bucket_late_ll_kernel(SyncPeers
     for (int j = tid; j < n_late4; j += stride) {
       const int i = (j < r.fc1_b4) ? j : j + early_n4;
       const float4 v = *reinterpret_cast<const float4*>(g_local + 4 * (size_t)i);
-      const uint4 l0 = make_uint4(__float_as_uint(v.x), tag, __float_as_uint(v.y), tag);
+      const uint4 l0 = BF16 ? make_uint4(pack_bf16x2(v.x, v.y), tag, pack_bf16x2(v.z, v.w), tag)
+                            : make_uint4(__float_as_uint(v.x), tag, __float_as_uint(v.y), tag);
       const uint4 l1 = make_uint4(__float_as_uint(v.z), tag, __float_as_uint(v.w), tag);
-      const size_t li = slot + 2 * (size_t)j;
+      const size_t li = slot + LPE * (size_t)j;
       if (r.mc_inbox != nullptr) {
         multimem_st_b128(reinterpret_cast<uint4*>(r.mc_inbox) + li, l0);
-        multimem_st_b128(reinterpret_cast<uint4*>(r.mc_inbox) + li + 1, l1);
+        if (!BF16) multimem_st_b128(reinterpret_cast<uint4*>(r.mc_inbox) + li + 1, l1);
       } else {
         for (int q = 0; q < NR; ++q) {
           if (q == a.rank) continue;
           st_peer_b128(reinterpret_cast<uint4*>(r.inbox[q]) + li, l0);
-          st_peer_b128(reinterpret_cast<uint4*>(r.inbox[q]) + li + 1, l1);
+          if (!BF16) st_peer_b128(reinterpret_cast<uint4*>(r.inbox[q]) + li + 1, l1);
         }
       }
     }
@@ -374,11 +380,15 @@ __global__ void __launch_bounds__(LATE2_THREADS) bucket_late_ll_kernel(SyncPeers
   const uint4* inbox = reinterpret_cast<const uint4*>(r.inbox[a.rank]);
   for (int j = tid; j < n_late4; j += stride) {
     const int i = (j < r.fc1_b4) ? j : j + early_n4;
-    const float4 own = *reinterpret_cast<const float4*>(g_local + 4 * (size_t)i);
+    float4 own = *reinterpret_cast<const float4*>(g_local + 4 * (size_t)i);
+    if (BF16) {                                     // my own contribution exactly as the others see it
+      const uint32_t p0 = pack_bf16x2(own.x, own.y), p1 = pack_bf16x2(own.z, own.w);
+      own = make_float4(bf16_lo(p0), bf16_hi(p0), bf16_lo(p1), bf16_hi(p1));
+    }
     float4 g[SYNC_MAX_RANKS];
     // all N-1 slots are polled TOGETHER: the loads of every replica's lines are in flight at once (a line that has just
     // landed from NVLink costs a full memory latency; polling the slots one after the other serialised 7 of those at N = 8)
-    const uint4* src = inbox + half + 2 * (size_t)j;
+    const uint4* src = inbox + half + LPE * (size_t)j;
     uint32_t pending = ((NR >= 32) ? 0xffffffffu : ((1u << NR) - 1u)) & ~(1u << a.rank);
 #pragma unroll
     for (int c = 0; c < SYNC_MAX_RANKS; ++c)
@@ -391,13 +401,14 @@ __global__ void __launch_bounds__(LATE2_THREADS) bucket_late_ll_kernel(SyncPeers
       for (int c = 0; c < SYNC_MAX_RANKS; ++c) {
         if ((pending >> c) & 1u) {
           l0[c] = ld_volatile_b128(src + (size_t)c * lines_per_slot);
-          l1[c] = ld_volatile_b128(src + (size_t)c * lines_per_slot + 1);
+          if (!BF16) l1[c] = ld_volatile_b128(src + (size_t)c * lines_per_slot + 1);
         }
       }
 #pragma unroll
       for (int c = 0; c < SYNC_MAX_RANKS; ++c) {
-        if (((pending >> c) & 1u) && l0[c].y == tag && l0[c].w == tag && l1[c].y == tag && l1[c].w == tag) {
-          g[c] = make_float4(__uint_as_float(l0[c].x), __uint_as_float(l0[c].z), __uint_as_float(l1[c].x), __uint_as_float(l1[c].z));
+        if (((pending >> c) & 1u) && l0[c].y == tag && l0[c].w == tag && (BF16 || (l1[c].y == tag && l1[c].w == tag))) {
+          g[c] = BF16 ? make_float4(bf16_lo(l0[c].x), bf16_hi(l0[c].x), bf16_lo(l0[c].z), bf16_hi(l0[c].z))
+                      : make_float4(__uint_as_float(l0[c].x), __uint_as_float(l0[c].z), __uint_as_float(l1[c].x), __uint_as_float(l1[c].z));
           pending &= ~(1u << c);
         }
       }
@@ -451,12 +462,13 @@ extern "C" {
 // phase 2 = late bucket + end of the step.
 //   ctrl/params/grads: tables of `nranks` peer pointers (index = rank);  g16 / inbox: same, for the bf16 fc1 gradient buffer
 //   and the late-bucket inbox (2 parities x nranks slots x (numel - fc1 numel) x 8 bytes: LL lines);  mc_*: NVLS multicast views
-//   or null;  late_ll: 1 = LL protocol for the late bucket (default), 0 = data + release flags.
+//   or null;  late_ll: 1 = LL protocol for the late bucket (default), 0 = data + release flags;  late_bf16: LL lines carry
+//   bf16 (default) or fp32 gradients.
 //   fc1_begin/fc1_end/numel in floats, all multiples of 8 / 8 / 4.
 int dm_bucket_sync(void* const* ctrl, void* const* params, void* const* grads, void* const* g16, void* const* inbox, int rank,
                    int nranks, int phase, long long fc1_begin, long long fc1_end, long long numel, float lr0,
                    float decay_rate, int decay_steps, double timeout_ms, void* shadow_bf16, int ctas, void* stream_,
-                   void* mc_g16, void* mc_inbox, int late_ll) {
+                   void* mc_g16, void* mc_inbox, int late_ll, int late_bf16) {
   using namespace dm;
   if (nranks < 1 || nranks > SYNC_MAX_RANKS || phase < 1 || phase > 4) return -1;
   if ((fc1_begin & 7) || (fc1_end & 7) || (numel & 3) || fc1_begin < 0 || fc1_end < fc1_begin || fc1_end > numel) return -2;
@@ -488,7 +500,8 @@ int dm_bucket_sync(void* const* ctrl, void* const* params, void* const* grads, v
     DM_CUDA_OK(cudaFuncSetAttribute(bucket_early_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     DM_CUDA_OK(cudaFuncSetAttribute(bucket_early_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     DM_CUDA_OK(cudaFuncSetAttribute(bucket_late_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    DM_CUDA_OK(cudaFuncSetAttribute(bucket_late_ll_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    DM_CUDA_OK(cudaFuncSetAttribute(bucket_late_ll_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    DM_CUDA_OK(cudaFuncSetAttribute(bucket_late_ll_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
   if (phase != 2) {
@@ -509,7 +522,8 @@ int dm_bucket_sync(void* const* ctrl, void* const* params, void* const* grads, v
   // large late bucket (the MLPs: megabytes) is bandwidth-bound and goes as plain data + release flags
   if (late_ll && (long long)n_late4 * 16 <= (1ll << 20)) {        // no in-kernel barrier: any grid size is safe
     if (grid > 296) grid = 296;
-    return (int)launch_kernel(bucket_late_ll_kernel, dim3(grid), dim3(LATE2_THREADS), 0, stream, P, a, r);
+    if (late_bf16) return (int)launch_kernel(bucket_late_ll_kernel<true>, dim3(grid), dim3(LATE2_THREADS), 0, stream, P, a, r);
+    return (int)launch_kernel(bucket_late_ll_kernel<false>, dim3(grid), dim3(LATE2_THREADS), 0, stream, P, a, r);
   }
   if (ctas >= 1 && grid > ctas) grid = ctas;
   if (grid > 148) grid = 148;                                     // all CTAs must be co-resident (in-kernel barrier)

@@ -68,6 +68,7 @@ class FusedBackend(Backend):
         self._status_hi = max(self._off[f] for f in self._STATUS) + 4
         self.debug_sync = debug_sync or os.environ.get("DMNIST_DEBUG_SYNC", "0") == "1"
         self.late_ll = os.environ.get("DMNIST_LATE_LL", "1") != "0"     # LL lines (data + tags in one store) for the late bucket
+        self.late_bf16 = os.environ.get("DMNIST_LATE_BF16", "1") != "0"  # ... carrying bf16 gradients (half the bytes)
         # host mirror of the status words: the kernel that closes a step stores them into page-locked host memory itself
         self._mirror = torch.zeros(4 * 8, dtype=torch.int32).pin_memory()
         check(self.lib.dm_sync_set_host_mirror(ctypes.c_void_p(self.ctrl.local_ptr), ctypes.c_void_p(self._mirror.data_ptr())),
@@ -255,7 +256,7 @@ class FusedBackend(Backend):
             ctypes.c_longlong(fc1_begin), ctypes.c_longlong(fc1_end), ctypes.c_longlong(params.numel()),
             ctypes.c_float(lr0), ctypes.c_float(decay_rate), int(decay_steps), ctypes.c_double(self.timeout_ms),
             ctypes.c_void_p(0 if self.shadow is None else self.shadow.data_ptr()), int(ctas), stream_ptr(stream),
-            ctypes.c_void_p(mc_g16), ctypes.c_void_p(mc_inbox), int(self.late_ll))
+            ctypes.c_void_p(mc_g16), ctypes.c_void_p(mc_inbox), int(self.late_ll), int(self.late_bf16))
         check(rc, "dm_bucket_sync(phase %d)" % phase)
 
     # ---- device-side interval mode (mode C, csrc/fused_interval.cu) ----------------------------------------------------------

@@ -44,6 +44,8 @@ def main():
         g16v.copy_(full[e0:e1].to(torch.bfloat16))
         # ---- oracle: NCCL all-reduce (fp32 sums); fc1: sum of the bf16-rounded gradients, rounded to bf16 once more ----
         late_sum = full[late_idx].clone()
+        if be.late_ll and be.late_bf16:
+            late_sum = late_sum.to(torch.bfloat16).float()        # the late bucket crosses the wire as bf16 LL lines
         fc1_sum = g16v.float().clone()
         if n > 1:
             dist.all_reduce(late_sum)

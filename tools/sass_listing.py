@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Committed SASS evidence: full instruction listings of the hot kernels of ``libdmnist_b200.so`` (``cuobjdump -sass``, hex
 encodings stripped) plus a per-kernel count of the mnemonics that prove a Blackwell-native kernel
-(``UTC*MMA`` = tcgen05.mma, ``LDTM``/``STTM`` = tcgen05.ld/st, ``UTMALDG``/``UBLKCP`` = TMA, ``LDGMC``/``STGMC``... = multimem,
-``SYNCS`` = mbarrier).  Runs here (no GPU):  ``python tools/sass_listing.py profiles/r2/sass``."""
+(``UTC*MMA`` = tcgen05.mma, ``LDTM``/``STTM`` = tcgen05.ld/st, ``UTMALDG``/``UBLKCP`` = TMA, ``LDGMC`` = multimem.ld_reduce (a ``multimem.st`` is an ordinary ``STG.E.128.STRONG.SYS`` whose
+ADDRESS is the multicast mapping), ``SYNCS`` = mbarrier).  Runs here (no GPU):  ``python tools/sass_listing.py profiles/r2/sass``."""
 import os
 import re
 import subprocess
@@ -18,7 +18,7 @@ HOT = [("conv2_fwd", r"conv2_fwd_kernelILi1E"), ("conv2_dgrad", r"conv2_dgrad_ke
        ("iv_apply", r"iv_apply_kernel")]
 KEY = [("tcgen05.mma", r"\bUTC[A-Z]*MMA"), ("tcgen05.ld", r"\bLDTM"), ("tcgen05.st", r"\bSTTM"), ("tcgen05.cp/alloc", r"\bUTC(CP|ATOMSWS|BAR)"),
        ("TMA tensor load", r"\bUTMALDG"), ("TMA bulk", r"\bUBLKCP"), ("mbarrier", r"\bSYNCS"), ("multimem ld_reduce", r"\bLDGMC|\bLD\S*\.MC|MULTIMEM|REDUX\.MC"),
-       ("multimem st", r"\bSTG\S*\.MC|\bSTGMC|\bST\S*\.MMC"), ("legacy HMMA (must be 0)", r"\bHMMA"), ("fence.sys", r"MEMBAR\S*\.SYS|FENCE\S*SYS"),
+       ("st.sys (incl. multimem.st)", r"\bSTG?\.E\S*\.STRONG\.SYS"), ("legacy HMMA (must be 0)", r"\bHMMA"), ("fence.sys", r"MEMBAR\S*\.SYS|FENCE\S*SYS"),
        ("sys-scope ld/st", r"\b(LD|ST)G?\S*\.SYS")]
 
 
