@@ -265,7 +265,10 @@ class CudaLeNetEngine(ComputeEngine):
             self._g16_view = self._g16.view(torch.bfloat16, 0, e1 - e0).view(*getattr(self, "_g16_shape", (3136, 512)))
             n_late = self.spec.arena_numel - (e1 - e0)
             self._inbox = self.backend.allocate_buffer(2 * n * n_late * 8) if n > 1 else None   # LL lines: 8 bytes per float
-        self._early_ctas = int(os.environ.get("DMNIST_EARLY_CTAS", "148"))
+        # early-bucket grid: the CTAs share SMs with the tensor-core kernels of the backward pass and every one of them fences
+        # at system scope once; measured at N = 4 (profiles/r2/bench_call12_4gpu.txt): 296 CTAs 90.8, 148 CTAs 85.8, 74 CTAs
+        # 82.5 us/step -- half the SMs carry the exchange, the kernel still ends before the backward pass does
+        self._early_ctas = int(os.environ.get("DMNIST_EARLY_CTAS", "0")) or (74 if n > 1 else 148)
         torch.cuda.synchronize()
         self._seq0 = self.backend.status_seq       # steps closed on this control block before the engine's first one
         self._steps_launched = 0

@@ -143,7 +143,15 @@ fi
 if has matrix; then
   # the reference's experiment matrices on this box: K-of-N sweep + interval sweep (time-to-accuracy, step rate, loss) and the
   # compute-time CDF study; figures + scraped logs land in gpurun_out/matrix_*
-  for m in ${MATRIX:-8_gpus time_cdf_cfgs}; do
+  if [ -n "${MATRIX_FILES:-}" ]; then
+    # explicit list of configuration files (budgeted runs)
+    timeout ${MATRIX_TIMEOUT:-600} python tools/benchmark.py select_files $MATRIX_FILES --n_iters=${MATRIX_ITERS:-19000} \
+        --outdir=gpurun_out/matrix_sel --dest=gpurun_out/matrix_sel > gpurun_out/matrix_sel.log 2>&1
+    echo "matrix (selected files) exit=$?"; grep -E "Currently on iteration|timeout waiting|Traceback|Error" gpurun_out/matrix_sel.log | head -40
+    grep -A14 "^File:" gpurun_out/matrix_sel.log | head -40; ls gpurun_out/matrix_sel | head -60
+    MATRIX=""
+  fi
+  for m in ${MATRIX-8_gpus time_cdf_cfgs}; do
     files=""
     for f in $(ls cfg/$m); do
       # MATRIX_SKIP: space-separated substrings of configuration names to leave out (budget)
