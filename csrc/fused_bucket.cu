@@ -222,7 +222,8 @@ __global__ void __launch_bounds__(LATE2_THREADS, 1) bucket_late_kernel(SyncPeers
   const float* g_local = P.grads[a.rank];
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const unsigned long long now = globaltimer_ns();
-    me->t_arrive[epoch % TIMING_RING] = now;     // "gradient complete" stamp: compute time excludes the barrier below
+    if (me->t_arrive[epoch % TIMING_RING] < me->t_start[epoch % TIMING_RING] || me->t_start[epoch % TIMING_RING] == 0)
+      me->t_arrive[epoch % TIMING_RING] = now;   // "gradient complete" stamp (unless the compute chain stamped it already)
     me->t_phase[0] = now;
     if (NR == 1) me->t_phase[1] = now;
   }
@@ -339,7 +340,8 @@ __global__ void __launch_bounds__(LATE2_THREADS) bucket_late_ll_kernel(SyncPeers
   const float* g_local = P.grads[a.rank];
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const unsigned long long now = globaltimer_ns();
-    me->t_arrive[epoch % TIMING_RING] = now;     // "gradient complete" stamp: compute time excludes the exchange below
+    if (me->t_arrive[epoch % TIMING_RING] < me->t_start[epoch % TIMING_RING] || me->t_start[epoch % TIMING_RING] == 0)
+      me->t_arrive[epoch % TIMING_RING] = now;   // "gradient complete" stamp (unless the compute chain stamped it already)
     me->t_phase[0] = now;
   }
   // line index space of an inbox: [2 parities][NR slots][2 * n_late4 lines of 16 bytes]

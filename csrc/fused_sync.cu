@@ -548,6 +548,13 @@ __global__ void device_barrier_kernel(SyncPeers P, int rank, int nranks, unsigne
 
 // Stamp the start of a step's compute (%globaltimer) for the cdf-mode telemetry.
 __global__ void stamp_start_kernel(SyncCtrl* ctrl) { ctrl->t_start[ctrl->epoch % TIMING_RING] = globaltimer_ns(); }
+// Stamp "my gradient is complete": launched on the compute chain after the last backward kernel and BEFORE the chain joins the
+// exchange branch, so a replica's compute time never contains the wait for a slower replica's gradients
+// (reference: finished - dequeued, src/timeout_manager.py:55-61).  The aggregation kernels keep an existing stamp of this step.
+__global__ void stamp_arrive_kernel(SyncCtrl* ctrl) {
+  pdl_wait();
+  ctrl->t_arrive[ctrl->epoch % TIMING_RING] = globaltimer_ns();
+}
 
 }  // namespace dm
 
@@ -683,6 +690,11 @@ int dm_device_barrier(void* const* ctrl, int rank, int nranks, double timeout_ms
   }
   device_barrier_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(P, rank, nranks, (unsigned long long)(timeout_ms * 1e6));
   return (int)cudaGetLastError();
+}
+
+int dm_stamp_arrive(void* ctrl, void* stream_) {
+  return (int)dm::launch_kernel(dm::stamp_arrive_kernel, dim3(1), dim3(1), 0, reinterpret_cast<cudaStream_t>(stream_),
+                                reinterpret_cast<dm::SyncCtrl*>(ctrl));
 }
 
 int dm_stamp_start(void* ctrl, void* stream_) {

@@ -358,7 +358,7 @@ class CudaLeNetEngine(ComputeEngine):
             ev_du.record(main)
             with torch.cuda.stream(self._side[0]):
                 self._side[0].wait_event(ev_du)
-                if self._straggler is not None:
+                if self._straggler is not None and not getattr(self, "_delay_in_chain", False):
                     self.backend.enqueue_straggler_delay(self._straggler.prob, self._straggler.usec, stream=self._side[0])
                 oa = self._opt_args
                 e0, e1 = self._bucket_early
@@ -398,8 +398,13 @@ class CudaLeNetEngine(ComputeEngine):
         check(conv1_wgrad(ptr(images), ptr(self.dx1), ptr(self.code1), ptr(g["conv1_weights"]),
                           ptr(g["conv1_biases"]), B, sp), "conv1_wgrad")
         if branch:
-            main.wait_event(join1)
             main.wait_event(join2)
+            if self._stamp and early_sync:
+                # every backward kernel of THIS replica is done (conv1_wgrad on the chain, conv2_wgrad joined): stamp it before
+                # waiting for the exchange branch, which contains the all-to-all with the other replicas
+                main.wait_event(join3)
+                self.backend.enqueue_stamp_arrive()
+            main.wait_event(join1)
             if early_sync:
                 main.wait_event(join3)
         return 6 if self._fuse_unpool else 7
@@ -487,16 +492,22 @@ class CudaLeNetEngine(ComputeEngine):
 
     def _launch_step(self, slot: int, with_sync: bool) -> None:
         n = 0
+        interval = with_sync and getattr(self, "_interval", False)
+        bucketed = with_sync and self._bucketed and not interval
+        self._delay_in_chain = False
         if self._stamp:
             self.backend.enqueue_stamp_start()
             n += 1
-        interval = with_sync and getattr(self, "_interval", False)
+            if bucketed and self._straggler is not None:
+                # cdf telemetry: the injected delay is part of THIS replica's compute (start stamp .. gradient-complete stamp)
+                self.backend.enqueue_straggler_delay(self._straggler.prob, self._straggler.usec)
+                self._delay_in_chain = True
+                n += 1
         if interval:
             self.backend.enqueue_interval_begin(self.params)
             n += 2
         n += self._launch_zero()
         n += self._launch_forward(self.images[slot], self.labels[slot], self.batch_size, True)
-        bucketed = with_sync and self._bucketed and not interval
         n += self._launch_backward(self.images[slot], self.batch_size, early_sync=bucketed)
         if bucketed:
             oa = self._opt_args

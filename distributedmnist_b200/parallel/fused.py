@@ -303,6 +303,10 @@ class FusedBackend(Backend):
             check(self.lib.dm_device_barrier(self.ctrl.ptr_table(), self.ctx.rank, self.ctx.world_size,
                                              ctypes.c_double(self.timeout_ms), stream_ptr(stream)), "dm_device_barrier")
 
+    def enqueue_stamp_arrive(self, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """cdf telemetry: "my gradient is complete" on the compute chain, before it joins the exchange branch."""
+        check(self.lib.dm_stamp_arrive(ctypes.c_void_p(self.ctrl.local_ptr), stream_ptr(stream)), "dm_stamp_arrive")
+
     def enqueue_stamp_start(self, stream: Optional[torch.cuda.Stream] = None) -> None:
         check(self.lib.dm_stamp_start(ctypes.c_void_p(self.ctrl.local_ptr), stream_ptr(stream)), "dm_stamp_start")
 

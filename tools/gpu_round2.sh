@@ -38,7 +38,7 @@ if has mgtests; then
   echo "pytest(multi-gpu) exit=$?" >> gpurun_out/pytest_multigpu.log; tail -30 gpurun_out/pytest_multigpu.log | cut -c1-400
 fi
 if has tests; then
-  timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
+  timeout ${TESTS_TIMEOUT:-1200} python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
   echo "pytest exit=$?" >> gpurun_out/pytest_gpu.log; tail -30 gpurun_out/pytest_gpu.log | cut -c1-400
 fi
 if has bench; then
@@ -47,9 +47,11 @@ if has bench; then
   SMI=$!
   run_bench --steps 300 --warmup 20 ${BENCH_ARGS:-} > gpurun_out/bench_ours_$GPUS.json 2> gpurun_out/bench_ours_$GPUS.err
   echo "bench ours exit=$?"; cat gpurun_out/bench_ours_$GPUS.json; grep -m1 KERNEL_TIMES gpurun_out/bench_ours_$GPUS.err; tail -3 gpurun_out/bench_ours_$GPUS.err
-  # the driver's own invocation: 20 timed steps
-  run_bench --steps 20 --warmup 5 > gpurun_out/bench_ours_${GPUS}_k20.json 2>> gpurun_out/bench_ours_$GPUS.err
-  echo "bench ours (20 steps, as the driver runs it) exit=$?"; python -c "import json,sys; d=json.loads(open('gpurun_out/bench_ours_${GPUS}_k20.json').read().strip().splitlines()[-1]); print('k20 ms_per_step', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'])"
+  if [ "${BENCH_K20:-1}" = "1" ]; then
+    # the driver's own invocation: 20 timed steps
+    run_bench --steps 20 --warmup 5 > gpurun_out/bench_ours_${GPUS}_k20.json 2>> gpurun_out/bench_ours_$GPUS.err
+    echo "bench ours (20 steps, as the driver runs it) exit=$?"; python -c "import json,sys; d=json.loads(open('gpurun_out/bench_ours_${GPUS}_k20.json').read().strip().splitlines()[-1]); print('k20 ms_per_step', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'])"
+  fi
   kill $SMI
 fi
 if has base; then
@@ -106,7 +108,7 @@ if has cdf; then
   # cdf mode (full barrier + per-iteration timing) with a device-side straggler on the last rank: the ELAPSED TIMES tables come
   # from the %globaltimer stamps of the step's kernels, so only the delayed rank shows a tail
   rm -rf /tmp/cdf_train; mkdir -p gpurun_out/cdf_$GPUS
-  run_py 300 src/mnist_distributed_train.py --job_name=worker --batch_size=256 --max_steps=520 --log_every=100 \
+  run_py ${CDF_TIMEOUT:-300} src/mnist_distributed_train.py --job_name=worker --batch_size=256 --max_steps=520 --log_every=100 \
       --worker_times_cdf_method=true --inject_straggler=$((GPUS-1)):0.3:300 --train_dir=/tmp/cdf_train --save_interval_secs=1000 \
       > gpurun_out/cdf_$GPUS/b256_straggler_${GPUS}gpu_out_master 2>&1
   echo "cdf exit=$?"; grep -c "ELAPSED TIMES" gpurun_out/cdf_$GPUS/b256_straggler_${GPUS}gpu_out_master
@@ -128,8 +130,8 @@ PY
 fi
 if has ncu; then
   # one full-set capture of every kernel of the (eager, un-graphed) step on ONE GPU; read here with tools/ncu_summary.py
-  timeout 900 ncu --set full --clock-control none --import-source on \
-      -k regex:'conv1_|conv2_|gemm_tc|fc2_|bucket_' -s 60 -c 36 \
+  timeout ${NCU_TIMEOUT:-900} ncu --set full --clock-control none --import-source on \
+      -k regex:'conv1_|conv2_|gemm_tc|fc2_|bucket_' -s ${NCU_SKIP:-60} -c ${NCU_COUNT:-36} \
       -f -o gpurun_out/lenet_step_r2 python bench.py --steps 3 --warmup 3 --no-graph > gpurun_out/ncu_full_run.log 2>&1
   echo "ncu full exit=$?"; ls -la gpurun_out/*.ncu-rep
 fi
