@@ -211,8 +211,14 @@ def _engine(B: int, seed: int = 5):
     return CudaLeNetEngine(B, be, seed=seed, rank=0, use_graph=False), be
 
 
-# per-tensor L2 bound of (bf16-operand tensor-core gradients) vs (fp32 reference gradients); see check_end_to_end
-FP32_GRAD_TOL = 1e9
+# Per-tensor L2 bound of (gradients of the bf16-operand tensor-core step) vs (gradients of a PLAIN fp32 model, TF32 off).
+# This is not a kernel-accuracy figure -- against the bf16-emulating reference every tensor agrees to <= 0.44 % (above) -- but
+# the distance between bf16 and fp32 *training arithmetic*: activations rounded to bf16 flip ReLU / max-pool decisions, and the
+# flips accumulate towards the input.  Measured on B200 (B = 64, seed 5; profiles/r2/): conv1_w 9.6 %, conv1_b 4.0 %,
+# conv2_w 4.9 %, conv2_b 3.8 %, fc1_w 3.5 %, fc1_b 3.5 %, fc2_w 0.47 %, fc2_b 0.36 %.  Bounds = ~3x those: a wrong tap, a
+# transposed tile or a dropped bias shows up as O(1).
+FP32_GRAD_TOLS = {"conv1_weights": 0.30, "conv1_biases": 0.15, "conv2_weights": 0.15, "conv2_biases": 0.15,
+                  "fc1_weights": 0.12, "fc1_biases": 0.12, "fc2_weights": 0.03, "fc2_biases": 0.03}
 
 
 def check_end_to_end(B: int = 64, seed: int = 5) -> List[Result]:
@@ -255,7 +261,7 @@ def check_end_to_end(B: int = 64, seed: int = 5) -> List[Result]:
     for name in r32:
         num = (gv[name].double() - r32[name].double()).norm().item()
         den = r32[name].double().norm().item() + 1e-12
-        out.append(("e2e.grad_vs_fp32.%s(L2 rel)" % name, num / den, FP32_GRAD_TOL))
+        out.append(("e2e.grad_vs_fp32.%s(L2 rel)" % name, num / den, FP32_GRAD_TOLS.get(name, 0.3)))
     out.append(("e2e.loss_vs_fp32", abs(loss - rloss32.item()), 0.02 * max(1.0, abs(rloss32.item()))))
     # padding of the gradient arena must stay zero (the fused kernel reduces the whole arena)
     out.append(("e2e.grad.padding", eng.grads[~spec.valid_mask().cuda()].abs().max().item(), 1e-12))
