@@ -28,13 +28,11 @@ def main():
             if q == r:
                 row.append("self")
                 continue
-            os.lseek(fd, 0, os.SEEK_SET)
-            row.append(os.read(fd, 100).decode())
+            row.append(os.pread(fd, 100, 0).decode())       # (a passed fd shares its file OFFSET with every other holder)
             os.close(fd)
         texts.append(row)
     b = chan.broadcast(f.fileno() if r == 0 else None, 0)
-    os.lseek(b, 0, os.SEEK_SET)
-    bc = os.read(b, 100).decode()
+    bc = os.pread(b, 100, 0).decode()
     ok = _all_ok(r != 1) if n > 1 else True                # rank 1 "fails" -> everybody must see False
     json.dump({"rank": r, "texts": texts, "bcast": bc, "all_ok": ok}, open(out_json, "w"))
     dist.barrier()
