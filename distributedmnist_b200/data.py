@@ -257,6 +257,12 @@ def read_data_sets(train_dir: str, fake_data: bool = False, one_hot: bool = Fals
         test_images = extract_data(paths[2], 10000)
         test_labels = extract_labels(paths[3], 10000)
     elif synthetic:
+        # Loud, because accuracy / time-to-accuracy numbers of a run on this data are NOT MNIST numbers (the generated
+        # classes are far easier); the only other sign would be the missing "Extracting ..." lines.
+        import logging
+        logging.getLogger("dmnist").warning(
+            "*** MNIST IDX files not found under %r: training on SYNTHETIC MNIST-shaped data (--synthetic_data=true). "
+            "Precision / loss / time-to-accuracy of this run are not MNIST results. ***" % train_dir)
         train_images, train_labels, test_images, test_labels = make_synthetic_mnist(
             synthetic_sizes[0], synthetic_sizes[1], seed=seed)
     else:

@@ -247,3 +247,160 @@ class BucketedExchange:
         assert all(v == ep for v in self.early_from[r]), "replica %d reads early-bucket shards of steps %s in step %d" % (r, self.early_from[r], ep)
         self._wait(self.done[r], ep + 1)
         self.epoch[r] = ep + 1
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Interval mode (mode C) -- executable model of csrc/fused_interval.cu
+# ----------------------------------------------------------------------------------------------------------------------
+class IntervalBoard:
+    """Word-level model of the device-side interval protocol (one thread per replica in tests; every method body is one
+    "memory operation" of the kernels and takes the lock, so threads interleave at exactly the granularity at which the
+    kernels' system-scope loads / stores / CAS interleave on the GPUs under sequentially consistent fences).
+
+    State per replica (the words of ``SyncCtrl``): ``epoch``, ``iv_state`` = (step tag, count), ``iv_busy``, the local copy of
+    the commit ring, ``done`` flags; the chief's authoritative ``commit`` ring.  The accumulator is modelled as a float per
+    replica plus an ``in_flight`` marker the committer must never observe while it reads (the property the Dekker pair
+    ``busy := step+1; fence; read commit``  ||  ``write commit; fence; read busy`` provides).
+    """
+
+    def __init__(self, num_replicas: int, lr: float = 1.0):
+        self.n = num_replicas
+        self.lr = lr
+        self._lock = threading.Lock()
+        self.epoch = [0] * self.n
+        self.state = [(1, 0)] * self.n             # (step + 1 tag, count)
+        self.busy = [0] * self.n
+        self.commit_local = [dict() for _ in range(self.n)]   # step -> (mask, committer)
+        self.done = [[0] * self.n for _ in range(self.n)]     # done[q][p]: p's pushes for step s landed on q (value s+1)
+        self.commit: Dict[int, tuple] = {}         # chief: step -> (mask, committer)
+        self.acc = [0.0] * self.n
+        self.in_flight = [False] * self.n
+        self.weights = [0.0] * self.n
+        self.ticks = []                            # (step, committer, mask, total)
+        self.dropped = [0] * self.n
+        self.accumulated = [0] * self.n
+        self.lost = [0] * self.n                   # accumulated for a step whose mask was frozen a moment earlier (count was 0)
+
+    # -- iv_adopt ------------------------------------------------------------------------------------------------------------
+    def adopt(self, r: int) -> int:
+        with self._lock:
+            e, adopted = self.epoch[r], 0
+            while e in self.commit_local[r]:
+                mask, committer = self.commit_local[r][e]
+                if self.done[r][committer] < e + 1:
+                    break                          # its pushes are still landing
+                tag, c = self.state[r]
+                if tag == e + 1 and c > 0 and not (mask >> r) & 1:
+                    self.lost[r] += c              # arrived after the mask was read: discarded with the step (reference: stale)
+                e += 1
+                adopted += 1
+            if adopted:
+                self.epoch[r] = e
+                self.state[r] = (e + 1, 0)
+            return adopted
+
+    # -- iv_gate: busy := step+1; fence; commit word present? ------------------------------------------------------------------
+    def gate_set_busy(self, r: int) -> int:
+        with self._lock:
+            self.busy[r] = self.epoch[r] + 1
+            return self.epoch[r]
+
+    def gate_check(self, r: int, e: int) -> bool:
+        with self._lock:
+            go = e not in self.commit_local[r]
+            if not go:
+                self.busy[r] = 0
+                self.dropped[r] += 1
+            return go
+
+    # -- iv_accumulate (two operations so a reader could observe it half done) ---------------------------------------------------
+    def accumulate_begin(self, r: int) -> None:
+        with self._lock:
+            self.in_flight[r] = True
+
+    def accumulate_end(self, r: int, g: float) -> None:
+        with self._lock:
+            first = self.state[r][1] == 0
+            self.acc[r] = g if first else self.acc[r] + g
+            self.in_flight[r] = False
+
+    # -- iv_close ---------------------------------------------------------------------------------------------------------------------
+    def close(self, r: int, e: int) -> None:
+        with self._lock:
+            tag, c = self.state[r]
+            assert tag == e + 1
+            self.state[r] = (tag, c + 1)
+            self.busy[r] = 0
+            self.accumulated[r] += 1
+
+    def try_commit(self, r: int, e: int) -> Optional[int]:
+        """Deadline passed: read every replica's state word, CAS the chief's commit word.  Returns the mask if this replica won."""
+        with self._lock:
+            if e in self.commit:
+                return None
+        mask = 0
+        for q in range(self.n):
+            with self._lock:                        # one remote load per replica
+                tag, c = self.state[q]
+            if tag == e + 1 and c > 0:
+                mask |= 1 << q
+        with self._lock:                            # the CAS
+            if e in self.commit:
+                return None
+            self.commit[e] = (mask, r)
+        for q in range(self.n):
+            with self._lock:                        # broadcast of the commit word, one store per replica
+                self.commit_local[q][e] = (mask, r)
+        return mask
+
+    def collect(self, r: int, e: int, mask: int) -> int:
+        """Committer: wait until no contributor is mid-accumulate for this step, then read the final counts."""
+        total = 0
+        for q in range(self.n):
+            if not (mask >> q) & 1:
+                continue
+            while True:
+                with self._lock:
+                    if self.busy[q] != e + 1:
+                        break
+                time.sleep(0)
+            with self._lock:
+                tag, c = self.state[q]
+                assert tag == e + 1, "a contributor moved on before its accumulator was read"
+                total += c
+        return total
+
+    # -- iv_apply ----------------------------------------------------------------------------------------------------------------------
+    def apply(self, r: int, e: int, mask: int, total: int) -> None:
+        s = 0.0
+        for q in range(self.n):
+            if (mask >> q) & 1:
+                with self._lock:
+                    assert not self.in_flight[q], "committer read an accumulator while its owner was adding to it"
+                    s += self.acc[q]
+        with self._lock:
+            new_w = self.weights[r] - self.lr * s / total
+        for q in range(self.n):
+            with self._lock:
+                self.weights[q] = new_w
+        with self._lock:
+            self.ticks.append((e, r, mask, total))
+        for q in range(self.n):
+            with self._lock:
+                self.done[q][r] = e + 1
+
+    # -- one local iteration of replica r (what the step graph does) -----------------------------------------------------------------------
+    def iteration(self, r: int, g: float, deadline_passed: bool, compute=lambda: None) -> None:
+        self.adopt(r)
+        compute()
+        e = self.gate_set_busy(r)
+        if not self.gate_check(r, e):
+            return
+        self.accumulate_begin(r)
+        self.accumulate_end(r, g)
+        self.close(r, e)
+        if deadline_passed:
+            mask = self.try_commit(r, e)
+            if mask is not None:
+                total = self.collect(r, e, mask)
+                self.apply(r, e, mask, total)

@@ -140,3 +140,52 @@ def test_bucketed_overlapped_exchange_model_is_race_free_and_matches_allreduce_s
         assert ex.epoch[r] == steps
         assert np.array_equal(ex.params[r], ex.params[0])           # replicas bit-identical
     assert np.allclose(ex.params[0], w_ref, atol=1e-5)
+
+
+def test_device_interval_protocol_model_accounts_every_gradient_exactly_once():
+    """Executable model of csrc/fused_interval.cu (parallel/protocol.py::IntervalBoard): free-running replicas, random
+    deadlines, one slow replica.  Every tick has exactly one committer; every computed gradient is either part of exactly one
+    tick's divisor or dropped as stale; the committer never reads an accumulator that is being added to; with a constant
+    gradient the weights are w0 - lr * (#ticks) * g on every replica (mean of ANY subset of equal gradients is that gradient)."""
+    import random
+    import threading
+    import time
+
+    from distributedmnist_b200.parallel.protocol import IntervalBoard
+    n, iters, g = 4, 300, 0.5
+    board = IntervalBoard(n, lr=0.1)
+    errors = []
+
+    def run(r):
+        rng = random.Random(100 + r)
+        try:
+            for _ in range(iters // (6 if r == n - 1 else 1)):
+                def compute():
+                    if r == n - 1:
+                        time.sleep(0.0005)            # the slow replica: several ticks per iteration
+                    elif rng.random() < 0.3:
+                        time.sleep(0)
+                board.iteration(r, g, deadline_passed=rng.random() < 0.25, compute=compute)
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(n)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(60)
+    assert not errors, errors
+    for r in range(n):
+        board.adopt(r)
+    steps = [t[0] for t in board.ticks]
+    assert sorted(steps) == list(range(len(steps))) and len(steps) > 10          # one committer per step, no gaps
+    assert all(total >= 1 and (mask >> committer) & 1 for (_s, committer, mask, total) in board.ticks)
+    # conservation: gradients accumulated = gradients counted in some tick + gradients left in never-committed accumulators
+    counted = sum(t[3] for t in board.ticks)
+    leftover = sum(c for (tag, c) in board.state)
+    # (+ the rare gradient that completed between the committer's read of its count (0) and the commit word reaching it)
+    assert sum(board.accumulated) == counted + leftover + sum(board.lost), (sum(board.accumulated), counted, leftover, board.lost)
+    assert len(set(board.epoch)) == 1 and board.epoch[0] == len(steps)
+    expect = -0.1 * len(steps) * g
+    assert all(abs(w - expect) < 1e-9 for w in board.weights), (board.weights, expect)
+    assert any(not (mask >> (n - 1)) & 1 for (_s, _c, mask, _t) in board.ticks)   # ticks committed without the slow replica
