@@ -369,7 +369,9 @@ def main():
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                        "samples": clocks["samples"]},
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms2_total / args.steps,
-                    "h2d_bytes_per_step": engine.h2d_bytes_per_step(), "d2h_bytes_per_step": 8,
+                    "h2d_bytes_per_step": engine.h2d_bytes_per_step(),
+                    # (loss, accuracy) copied by a graph branch + the 8 status words the closing kernel stores into host memory
+                    "d2h_bytes_per_step": 8 + 32,
                     "last_loss": last_loss},
             "backup_workers": (None if k == n else
                                {"k": k, "n": n, "window_global_steps": args.steps, "accepted_images_device_phase": images_dev,
