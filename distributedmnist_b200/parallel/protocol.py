@@ -404,3 +404,184 @@ class IntervalBoard:
             if mask is not None:
                 total = self.collect(r, e, mask)
                 self.apply(r, e, mask, total)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# K == N, bucketed (default path) -- executable model of csrc/fused_bucket.cu, explorable schedule by schedule
+# ----------------------------------------------------------------------------------------------------------------------
+class ProtocolHazard(AssertionError):
+    """A replica consumed data of another step, or overwrote data its consumer had not read yet."""
+
+
+class BucketV2Model:
+    """Word-level model of ``bucket_early_kernel`` + ``bucket_late_ll_kernel`` (csrc/fused_bucket.cu).
+
+    Every replica is a generator; each ``yield`` is one memory operation visible to the other replicas (a flag store, the
+    loads of one element from all peers, the stores of one element to one peer, one LL line landing at ONE destination -- a
+    multicast store reaches its destinations at different times) or a blocking wait (``yield predicate``).  A scheduler
+    picks which runnable replica performs its next operation, so a test can enumerate EVERY interleaving of a small instance
+    (:func:`explore_schedules`) or sample large ones.  The memory cells carry (step, kind) tags next to their values and every
+    read checks them: the model fails with :class:`ProtocolHazard` exactly when the kernels would consume torn / stale data.
+
+    What the model is for -- the three places where the kernels rely on an ordering argument instead of a flag:
+
+    * the LL inbox has no "consumed" handshake: slot ``[parity][sender]`` is rewritten two steps later.  Safe because a sender
+      can only reach step s + 2 after it received every peer's step s + 1 lines, which a peer sends only after its step-s
+      kernel (and therefore its step-s polls) completed.  ``parities=1`` removes the double buffer and must fail.
+    * the in-place reduction of the bf16 early bucket: rank r overwrites shard r of EVERY replica's buffer with the sum.  A
+      replica may read its whole buffer only after ``done_e`` of all ranks, and may start the next backward pass (which
+      overwrites the buffer with new gradients) only then too.  ``wait_done_e=False`` must fail.
+    * gradients are read from peers only after ``arrive_e`` of that peer (``wait_arrive_e=False`` must fail).
+    """
+
+    def __init__(self, n: int, early_len: int, late_len: int, steps: int, parities: int = 2, wait_arrive_e: bool = True,
+                 wait_done_e: bool = True, lr: float = 0.5):
+        self.n, self.early_len, self.late_len, self.steps, self.parities, self.lr = n, early_len, late_len, steps, parities, lr
+        self.wait_arrive_e, self.wait_done_e = wait_arrive_e, wait_done_e
+        self.w_early = [[0.0] * early_len for _ in range(n)]
+        self.w_late = [[0.0] * late_len for _ in range(n)]
+        self.g16 = [[(-1, "none", 0.0)] * early_len for _ in range(n)]            # (step, "raw" | "sum", value)
+        self.inbox = [[[[(0, 0.0)] * late_len for _ in range(n)] for _ in range(parities)] for _ in range(n)]   # [dst][parity][src][i] = (tag, v)
+        self.consumed = [[[[0] * late_len for _ in range(n)] for _ in range(parities)] for _ in range(n)]      # highest tag dst has read
+        self.arrive_e = [[0] * n for _ in range(n)]      # [owner][peer]
+        self.done_e = [[0] * n for _ in range(n)]
+        self.epoch = [0] * n
+
+    @staticmethod
+    def grad(r: int, step: int, i: int, late: bool) -> float:
+        return float((r + 1) * (step + 1) + 3 * i + (100 if late else 0))         # small integers: sums are exact
+
+    def expected(self, late: bool, i: int) -> float:
+        return -self.lr / self.n * sum(self.grad(r, s, i, late) for r in range(self.n) for s in range(self.steps))
+
+    # -- one replica ------------------------------------------------------------------------------------------------------
+    def replica(self, r: int):
+        n = self.n
+        shard = (self.early_len + n - 1) // n
+        b, e = min(r * shard, self.early_len), min((r + 1) * shard, self.early_len)
+        for _ in range(self.steps):
+            ep = self.epoch[r]
+            # fc1_wgrad epilogue: my bf16 gradient of this step (local stores, but peers will read / overwrite these cells)
+            for i in range(self.early_len):
+                st, kind, _v = self.g16[r][i]
+                if st == ep - 1 and kind == "raw" and ep > 0:
+                    raise ProtocolHazard("replica %d starts step %d before shard of element %d was reduced" % (r, ep, i))
+                self.g16[r][i] = (ep, "raw", self.grad(r, ep, i, False))
+            if self.early_len:
+                yield None
+                # ---- bucket_early_kernel: exchange (operations on my own memory are not scheduling points of their own) ----------
+                for q in range(n):
+                    self.arrive_e[q][r] = ep + 1
+                    if q != r:
+                        yield None
+                if self.wait_arrive_e:
+                    yield (lambda: all(v >= ep + 1 for v in self.arrive_e[r]))
+                for i in range(b, e):
+                    total = 0.0
+                    for q in range(n):                   # multimem.ld_reduce / N peer loads
+                        st, kind, v = self.g16[q][i]
+                        if (st, kind) != (ep, "raw"):
+                            raise ProtocolHazard("replica %d reduced element %d of replica %d holding %s of step %d in step %d"
+                                                 % (r, i, q, kind, st, ep))
+                        total += v
+                    self.g16[r][i] = (ep, "sum", total)  # (the kernel writes its own copy through the local path)
+                    yield None
+                    for q in range(n):                   # multimem.st: lands per destination
+                        if q != r:
+                            self.g16[q][i] = (ep, "sum", total)
+                            yield None
+                for q in range(n):
+                    self.done_e[q][r] = ep + 1
+                    if q != r:
+                        yield None
+                # ---- apply --------------------------------------------------------------------------------------------------
+                if self.wait_done_e:
+                    yield (lambda: all(v >= ep + 1 for v in self.done_e[r]))
+                for i in range(self.early_len):
+                    st, kind, v = self.g16[r][i]
+                    if (st, kind) != (ep, "sum"):
+                        raise ProtocolHazard("replica %d applied element %d holding %s of step %d in step %d" % (r, i, kind, st, ep))
+                    self.w_early[r][i] -= self.lr / n * v
+                yield None
+            # ---- bucket_late_ll_kernel: push lines, poll, rank-ordered sum, SGD, epoch + 1 -----------------------------------------
+            tag, par = ep + 1, ep % self.parities
+            for q in range(n):
+                if q == r:
+                    continue
+                for i in range(self.late_len):
+                    old_tag = self.inbox[q][par][r][i][0]
+                    if self.consumed[q][par][r][i] < old_tag:
+                        raise ProtocolHazard("replica %d overwrote line %d (tag %d) in replica %d's inbox before it was read"
+                                             % (r, i, old_tag, q))
+                    self.inbox[q][par][r][i] = (tag, self.grad(r, ep, i, True))
+                yield None
+            for i in range(self.late_len):
+                yield (lambda i=i: all(self.inbox[r][par][c][i][0] >= tag for c in range(n) if c != r))
+                acc = 0.0
+                for c in range(n):
+                    if c == r:
+                        acc += self.grad(r, ep, i, True)
+                        continue
+                    t, v = self.inbox[r][par][c][i]
+                    if t != tag:
+                        raise ProtocolHazard("replica %d polled line %d of replica %d: tag %d, wanted %d (overwritten)" % (r, i, c, t, tag))
+                    self.consumed[r][par][c][i] = t
+                    acc += v
+                self.w_late[r][i] -= self.lr / n * acc
+            self.epoch[r] = ep + 1
+
+    # -- scheduler ----------------------------------------------------------------------------------------------------------
+    def run(self, choose) -> None:
+        """``choose(runnable_ranks) -> rank``.  Raises ``ProtocolHazard`` on a violated invariant or a deadlock."""
+        gens = {r: self.replica(r) for r in range(self.n)}
+        waiting = {}
+        for r in list(gens):
+            self._advance(r, gens, waiting)
+        while gens:
+            runnable = [r for r in sorted(gens) if r not in waiting or waiting[r]()]
+            if not runnable:
+                raise ProtocolHazard("deadlock: replicas %s wait forever (epochs %s)" % (sorted(gens), self.epoch))
+            r = choose(runnable)
+            waiting.pop(r, None)
+            self._advance(r, gens, waiting)
+        for r in range(self.n):
+            for i in range(self.early_len):
+                if self.w_early[r][i] != self.expected(False, i):
+                    raise ProtocolHazard("replica %d early weight %d = %r, expected %r" % (r, i, self.w_early[r][i], self.expected(False, i)))
+            for i in range(self.late_len):
+                if self.w_late[r][i] != self.expected(True, i):
+                    raise ProtocolHazard("replica %d late weight %d = %r, expected %r" % (r, i, self.w_late[r][i], self.expected(True, i)))
+
+    @staticmethod
+    def _advance(r, gens, waiting) -> None:
+        try:
+            w = next(gens[r])
+        except StopIteration:
+            del gens[r]
+            return
+        if w is not None:
+            waiting[r] = w
+
+
+def explore_schedules(make_model, max_runs: int = 200000) -> int:
+    """Run ``make_model().run`` under EVERY schedule (depth-first over the scheduler's choice points, replaying prefixes).
+    Returns the number of complete schedules; raises the first ``ProtocolHazard``."""
+    stack, runs = [[]], 0
+    while stack:
+        prefix = stack.pop()
+        trace = []
+
+        def choose(runnable, prefix=prefix, trace=trace):
+            i = len(trace)
+            c = prefix[i] if i < len(prefix) else 0
+            trace.append((c, len(runnable)))
+            return runnable[c]
+
+        make_model().run(choose)
+        runs += 1
+        if runs > max_runs:
+            raise RuntimeError("more than %d schedules" % max_runs)
+        for i in range(len(prefix), len(trace)):
+            for alt in range(1, trace[i][1]):
+                stack.append([t[0] for t in trace[:i]] + [alt])
+    return runs

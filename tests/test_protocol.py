@@ -189,3 +189,46 @@ def test_device_interval_protocol_model_accounts_every_gradient_exactly_once():
     expect = -0.1 * len(steps) * g
     assert all(abs(w - expect) < 1e-9 for w in board.weights), (board.weights, expect)
     assert any(not (mask >> (n - 1)) & 1 for (_s, _c, mask, _t) in board.ticks)   # ticks committed without the slow replica
+
+
+# ---- csrc/fused_bucket.cu (default K == N path): every interleaving of small instances, sampled large ones -----------------------
+def test_bucket_v2_ll_inbox_is_safe_under_every_schedule_of_two_replicas():
+    from distributedmnist_b200.parallel.protocol import BucketV2Model, explore_schedules
+    runs = explore_schedules(lambda: BucketV2Model(n=2, early_len=0, late_len=1, steps=4))
+    assert runs > 50, runs
+
+
+def test_bucket_v2_early_and_late_buckets_every_schedule_one_step_two_replicas():
+    from distributedmnist_b200.parallel.protocol import BucketV2Model, explore_schedules
+    runs = explore_schedules(lambda: BucketV2Model(n=2, early_len=2, late_len=1, steps=1), max_runs=2000000)
+    assert runs > 1000, runs
+
+
+def test_bucket_v2_sampled_schedules_up_to_eight_replicas():
+    import random
+
+    from distributedmnist_b200.parallel.protocol import BucketV2Model
+    for seed in range(60):
+        rng = random.Random(seed)
+        n = rng.choice([2, 3, 4, 8])
+        m = BucketV2Model(n=n, early_len=rng.choice([n, n + 1, 2 * n]), late_len=rng.choice([1, 3]), steps=rng.choice([3, 4, 5]))
+        mode = seed % 3
+        if mode == 0:
+            m.run(lambda runnable: rng.choice(runnable))
+        elif mode == 1:
+            m.run(lambda runnable: runnable[0])              # lowest rank runs as far ahead as the protocol lets it
+        else:
+            m.run(lambda runnable: runnable[-1])
+
+
+def test_bucket_v2_model_detects_the_hazards_the_kernels_guard_against():
+    from distributedmnist_b200.parallel.protocol import BucketV2Model, ProtocolHazard, explore_schedules
+    # single-buffered inbox: the fast replica's step s + 1 lines overwrite unread step-s lines
+    with pytest.raises(ProtocolHazard, match="overwrote line|overwritten|deadlock"):
+        explore_schedules(lambda: BucketV2Model(n=2, early_len=0, late_len=1, steps=3, parities=1))
+    # no wait for the peers' "my shard is out" flags: a replica applies un-reduced elements
+    with pytest.raises(ProtocolHazard, match="applied element|reduced element|before shard"):
+        BucketV2Model(n=2, early_len=2, late_len=1, steps=2, wait_done_e=False).run(lambda runnable: runnable[-1])
+    # no wait for the peers' "gradient written" flags: a replica reduces a peer's previous-step buffer
+    with pytest.raises(ProtocolHazard, match="reduced element"):
+        BucketV2Model(n=2, early_len=2, late_len=1, steps=2, wait_arrive_e=False).run(lambda runnable: runnable[0])
