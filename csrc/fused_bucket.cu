@@ -10,12 +10,16 @@
 //       so each GPU moves |g16| (1 + 1/N) bytes per direction instead of 2x that in fp32.  After the all-to-all "my shard is
 //       out" flags every rank applies SGD to ITS OWN fp32 master copy of fc1 from the now identical bf16 sum (master weights
 //       never cross NVLink) and rewrites the bf16 shadow the tensor-core kernels read.  All of it runs under the backward pass.
-//   bucket_late_kernel    end of the step; the only exposed communication.
-//       The small bucket (conv1/conv2/fc2 parameters + all biases, 236 KB) is PUSHED: every rank multicasts its gradients
-//       into slot [rank] of every replica's inbox (`multimem.st`; peer stores without NVLS), then one release flag per peer.
-//       A rank waits for the N flags, sums the N inbox slots in rank order (bit-identical everywhere) and applies SGD
-//       locally.  One NVLink hop (data + flag) instead of flag hop + load round trip + "done reading" hop; the inbox is
-//       double-buffered on the parity of the global step, so no rank ever waits for a peer to finish *reading*.
+//   bucket_late_ll_kernel end of the step; the only exposed communication (default for a late bucket <= 1 MB: LeNet, 236 KB).
+//       The small bucket (conv1/conv2/fc2 parameters + all biases) is PUSHED as LL lines {bf16x2, tag, bf16x2, tag} with
+//       tag = step + 1: every rank multicasts its lines into slot [rank] of every replica's inbox (`multimem.st`; peer stores
+//       without NVLS) and polls its own inbox until all N - 1 slots carry this step's tag -- data and "it is there" arrive in
+//       the same 16-byte store, so ONE NVLink store latency is exposed: no flags, no fences, no grid barrier.  Rank-ordered
+//       sum (bit-identical everywhere), SGD locally.  The inbox is double-buffered on the parity of the global step, so no
+//       rank ever waits for a peer to finish *reading* (why that is safe: parallel/protocol.py::BucketV2Model, explored
+//       schedule by schedule in tests/test_protocol.py).
+//   bucket_late_kernel    the same push with plain fp32 data + one release flag per peer: for late buckets of megabytes (the
+//       MLPs), which are bandwidth-bound -- LL lines would double their bytes.
 //
 // Replicas stay bit-identical: every rank applies the same bf16 sums / the same rank-ordered fp32 sums to identical weights.
 #include "fused_sync.cuh"
