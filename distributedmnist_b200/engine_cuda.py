@@ -31,7 +31,7 @@ from typing import Optional, Tuple
 import numpy as np
 import torch
 
-from .engine import ComputeEngine, TorchEngine
+from .engine import ComputeEngine
 from .models import get_model
 from .models.lenet import dropout_seed_mix
 from .ops import gemm as G

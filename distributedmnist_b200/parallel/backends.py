@@ -29,7 +29,7 @@ import torch
 import torch.distributed as dist
 
 from .context import ReplicaContext
-from .protocol import Decision, StoreCommitBoard, popcount
+from .protocol import Decision, StoreCommitBoard
 
 
 @dataclass

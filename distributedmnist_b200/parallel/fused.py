@@ -332,7 +332,6 @@ class FusedBackend(Backend):
     def interval_tick(self, params, acc, count, lr, tick) -> StepInfo:
         """Mode C tick: every rank joins; ranks with an empty accumulator contribute zeros and the
         divisor is the total number of accumulated gradients (mean of whatever arrived)."""
-        import torch.distributed as dist
         counts = self.all_gather_object(int(count))
         total = sum(counts)
         mask = sum(1 << i for i, c in enumerate(counts) if c > 0)

@@ -11,7 +11,7 @@ from __future__ import annotations
 import math
 import struct
 import zlib
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import numpy as np
 
