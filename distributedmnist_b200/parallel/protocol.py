@@ -585,3 +585,181 @@ def explore_schedules(make_model, max_runs: int = 200000) -> int:
             for alt in range(1, trace[i][1]):
                 stack.append([t[0] for t in trace[:i]] + [alt])
     return runs
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# K < N (backup workers) -- word-level model of decide<KOFN> + fused_sync_sgd_kernel (csrc/fused_sync.cu)
+# ----------------------------------------------------------------------------------------------------------------------
+class KofNModel:
+    """Every replica is a generator over the memory operations of its training loop (same scheduler as
+    :class:`BucketV2Model`): read the parameter arena element by element (forward/backward), write the gradient arena, then
+    the kernel -- local commit word, ``atomicOr`` into the chief's bitmap slot, CAS on the chief's commit word by whoever
+    sees ``popcount >= K``, ``last_in_mask`` / ``global_step`` / broadcast of the commit word / wipe of the bitmap slot half
+    a ring ahead, reduction of the owned shard over the masked contributors, push of the new weights to ALL replicas,
+    ``done`` flags, the waits, fast-forward of late and stale replicas.
+
+    Invariants checked while it runs (``ProtocolHazard`` otherwise):
+
+    * a gradient that is ACCEPTED for step s was computed on exactly the weights of step s (a replica whose arena is being
+      pushed into while it computes must always turn out late);
+    * a team member only reads gradient arenas holding step-s gradients, and only pushes version s + 1 over version s;
+    * the committed mask contains only replicas that really arrived for that step (no phantom bit from a recycled bitmap slot);
+    * at the end every replica holds the same weights: the serial application of the committed means.
+
+    The bitmap slots carry no tag (one ``atomicOr`` per arrival instead of a CAS loop); the committer of step s wipes the slot
+    of step s + ring/2.  A replica that stalls for more than ring/2 global steps BETWEEN its commit-word read and its
+    ``atomicOr`` therefore leaves a phantom bit -- with the shipped ring of 64 that is a stall of > 32 steps (~4 ms) between
+    two instructions of one warp; the model shows it with ``ring=2`` (``tests/test_protocol.py``).
+    """
+
+    def __init__(self, n: int, k: int, steps: int, ring: int = 8, numel: Optional[int] = None, lr: float = 0.5):
+        assert 1 <= k <= n and ring >= 2 and ring % 2 == 0
+        self.n, self.k, self.steps, self.ring, self.lr = n, k, steps, ring, lr
+        self.numel = numel if numel is not None else n
+        self.full = (1 << n) - 1
+        self.params = [[(0, 0.0)] * self.numel for _ in range(n)]          # (version = number of updates applied, value)
+        self.grads = [(-1, False, None)] * n                                # (step, computed on consistent step weights, values)
+        self.epoch = [0] * n
+        self.arrived = [-1] * n                                             # last step a replica ORed its bit for
+        self.commit_local = [[(0, 0)] * ring for _ in range(n)]            # (tag, mask)
+        self.done = [[0] * n for _ in range(n)]                             # [owner][peer]
+        self.bitmap = [0] * ring                                            # chief
+        self.commit = [(0, 0)] * ring                                       # chief
+        self.last_in_mask = [0] * n                                         # chief
+        self.global_step = 0                                                # chief
+        self.log: Dict[int, int] = {}                                       # step -> committed mask
+        self.at = [""] * n                                                  # program point labels for targeted schedulers
+        self.accepted = [0] * n
+        self.dropped = [0] * n
+
+    @staticmethod
+    def grad(r: int, step: int, i: int) -> float:
+        return float((r + 1) + 7 * step + 3 * i)
+
+    def replica(self, r: int):
+        n, ring, bit = self.n, self.ring, 1 << r
+        while self.epoch[r] < self.steps:
+            ep = self.epoch[r]
+            # ---- forward / backward on my parameter arena (peers may push into it concurrently) -------------------------------
+            consistent = True
+            for i in range(self.numel):
+                consistent = consistent and self.params[r][i][0] == ep
+                yield None
+            self.grads[r] = (ep, consistent, [self.grad(r, ep, i) for i in range(self.numel)])
+            yield None
+            # ---- decide<KOFN> ----------------------------------------------------------------------------------------------
+            slot, want = ep % ring, ep + 1
+            cw = self.commit_local[r][slot]
+            self.at[r] = "after_commit_word_read"
+            yield None
+            self.at[r] = ""
+            if cw[0] < want:
+                self.bitmap[slot] |= bit                                    # atomicOr_system
+                self.arrived[r] = ep
+                now = self.bitmap[slot] & self.full
+                yield None
+                if popcount(now) >= self.k:
+                    old = self.commit[slot]
+                    yield None
+                    if old[0] < want:
+                        won = self.commit[slot] == old                      # atomicCAS_system
+                        if won:
+                            for q in range(n):
+                                if (now >> q) & 1 and self.arrived[q] != ep:
+                                    raise ProtocolHazard("step %d committed with a phantom bit of replica %d (it last arrived for step %d)"
+                                                         % (ep, q, self.arrived[q]))
+                            self.commit[slot] = (want, now)
+                            self.log[ep] = now
+                        yield None
+                        if won:
+                            for q in range(n):
+                                if (now >> q) & 1:
+                                    self.last_in_mask[q] = ep + 1
+                            yield None
+                            self.global_step = max(self.global_step, ep + 1)
+                            yield None
+                            for q in range(n):
+                                self.commit_local[q][slot] = (want, now)
+                                if q != r:
+                                    yield None
+                            self.bitmap[(slot + ring // 2) % ring] = 0
+                            yield None
+                yield (lambda: self.commit_local[r][slot][0] >= want)
+                cw = self.commit_local[r][slot]
+            if cw[0] == want:
+                mask, late = cw[1], not (cw[1] & bit)
+            else:
+                mask, late = 0, True                                        # committed a ring lap ago
+            target = ep + 1
+            if late:
+                g = self.global_step
+                yield None
+                target = max(g, ep + 1)
+            count = popcount(mask)
+            if not late:
+                step_g, ok, _vals = self.grads[r]
+                if not ok:
+                    raise ProtocolHazard("replica %d: gradient accepted for step %d was computed on weights of mixed steps" % (r, ep))
+                # ---- reduce my shard over the contributors, SGD, push to every replica -----------------------------------------
+                members = [q for q in range(n) if (mask >> q) & 1]
+                my_idx = members.index(r)
+                shard = (self.numel + count - 1) // count
+                for i in range(my_idx * shard, min((my_idx + 1) * shard, self.numel)):
+                    acc = 0.0
+                    for q in members:
+                        gs, _ok, vals = self.grads[q]
+                        if gs != ep:
+                            raise ProtocolHazard("replica %d read replica %d's gradient arena of step %d in step %d" % (r, q, gs, ep))
+                        acc += vals[i]
+                    yield None
+                    ver, w = self.params[r][i]
+                    if ver != ep:
+                        raise ProtocolHazard("replica %d updates element %d at version %d in step %d" % (r, i, ver, ep))
+                    new = (ep + 1, w - self.lr / count * acc)
+                    for q in range(n):
+                        if q != r and self.params[q][i][0] != ep:
+                            raise ProtocolHazard("replica %d pushes step %d over version %d of element %d at replica %d"
+                                                 % (r, ep, self.params[q][i][0], i, q))
+                        self.params[q][i] = new
+                        if q != r:
+                            yield None
+                for q in range(n):
+                    self.done[q][r] = ep + 1
+                    if q != r:
+                        yield None
+                self.accepted[r] += 1
+            else:
+                self.dropped[r] += 1
+            # ---- wait until every team member's shard has landed in MY arena ------------------------------------------------------
+            for q in range(n):
+                need = (ep + 1) if (mask >> q) & 1 else 0
+                if late:
+                    need = self.last_in_mask[q]                             # fast-forward: everything committed so far
+                    yield None
+                yield (lambda q=q, need=need: self.done[r][q] >= need)
+            self.epoch[r] = target
+
+    def run(self, choose) -> None:
+        gens = {r: self.replica(r) for r in range(self.n)}
+        waiting = {}
+        for r in list(gens):
+            BucketV2Model._advance(r, gens, waiting)
+        while gens:
+            runnable = [r for r in sorted(gens) if r not in waiting or waiting[r]()]
+            if not runnable:
+                raise ProtocolHazard("deadlock: replicas %s wait forever (epochs %s, global step %d)" % (sorted(gens), self.epoch, self.global_step))
+            r = choose(runnable)
+            waiting.pop(r, None)
+            BucketV2Model._advance(r, gens, waiting)
+        # serial replay of the committed means
+        assert sorted(self.log) == list(range(self.steps)), "committed steps %s" % sorted(self.log)
+        w = [0.0] * self.numel
+        for s in range(self.steps):
+            members = [q for q in range(self.n) if (self.log[s] >> q) & 1]
+            if len(members) < self.k:
+                raise ProtocolHazard("step %d committed with %d < K contributors" % (s, len(members)))
+            for i in range(self.numel):
+                w[i] -= self.lr / len(members) * sum(self.grad(q, s, i) for q in members)
+        for r in range(self.n):
+            if self.params[r] != [(self.steps, v) for v in w]:
+                raise ProtocolHazard("replica %d ends with %s, expected versions %d values %s" % (r, self.params[r], self.steps, w))

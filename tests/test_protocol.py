@@ -232,3 +232,46 @@ def test_bucket_v2_model_detects_the_hazards_the_kernels_guard_against():
     # no wait for the peers' "gradient written" flags: a replica reduces a peer's previous-step buffer
     with pytest.raises(ProtocolHazard, match="reduced element"):
         BucketV2Model(n=2, early_len=2, late_len=1, steps=2, wait_arrive_e=False).run(lambda runnable: runnable[0])
+
+
+# ---- csrc/fused_sync.cu (K < N): word-level model, sampled schedules with stragglers ---------------------------------------------
+def _kofn_run(seed: int, ring: int, stall_at_commit_word: bool):
+    import random
+
+    from distributedmnist_b200.parallel.protocol import KofNModel
+    rng = random.Random(seed)
+    n = rng.choice([2, 3, 4, 8])
+    k = rng.randint(1, n - 1) if stall_at_commit_word else rng.randint(1, n)
+    m = KofNModel(n, k, steps=rng.choice([3, 6, 12]), ring=ring)
+    victim, p = n - 1, rng.choice([0.01, 0.05, 0.3, 1.0])
+
+    def choose(runnable):
+        others = [r for r in runnable if r != victim]
+        if stall_at_commit_word:      # freeze the victim between its commit-word read and its atomicOr while the others run on
+            if victim in runnable and m.at[victim] == "after_commit_word_read" and others and rng.random() < 0.97:
+                return rng.choice(others)
+            return rng.choice(runnable)
+        if victim in runnable and others and rng.random() >= p:       # a straggler: scheduled with probability p
+            return rng.choice(others)
+        return rng.choice(runnable)
+
+    m.run(choose)
+    return m
+
+
+def test_kofn_word_level_model_accepts_only_consistent_gradients_and_replicas_converge():
+    accepted = dropped = 0
+    for seed in range(500):
+        m = _kofn_run(seed, ring=[4, 8, 64][seed % 3], stall_at_commit_word=False)
+        accepted += sum(m.accepted)
+        dropped += sum(m.dropped)
+    assert accepted > 1000 and dropped > 1000, (accepted, dropped)      # both the team path and the late / stale path ran
+
+
+def test_kofn_bitmap_ring_tolerates_stalls_below_half_a_lap_and_the_model_sees_longer_ones():
+    from distributedmnist_b200.parallel.protocol import ProtocolHazard
+    for seed in range(150):
+        _kofn_run(seed, ring=64, stall_at_commit_word=True)              # 12 steps can never lap half of the shipped ring
+    with pytest.raises(ProtocolHazard, match="phantom bit"):
+        for seed in range(150):
+            _kofn_run(seed, ring=2, stall_at_commit_word=True)
