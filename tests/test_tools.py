@@ -152,3 +152,39 @@ def test_summary_writer_emits_a_tensorboard_event_file(tmp_path):
     bad.write_bytes(bytes(raw))
     with pytest.raises(ValueError):
         read_tfevents(str(bad))
+
+
+def test_shipped_cfg_matrix_is_what_the_generator_writes(tmp_path, monkeypatch):
+    """cfg/** is generated (tools/make_cfgs.py); a hand edit of either side must not go unnoticed."""
+    import filecmp
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_cfgs", os.path.join(ROOT, "tools", "make_cfgs.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    monkeypatch.setattr(mod, "ROOT", str(tmp_path))
+    mod.main()
+    generated = sorted(os.path.relpath(os.path.join(d, f), str(tmp_path)) for d, _s, fs in os.walk(str(tmp_path)) for f in fs)
+    assert len(generated) >= 17
+    for rel in generated:
+        assert filecmp.cmp(os.path.join(str(tmp_path), rel), os.path.join(ROOT, rel), shallow=False), rel
+
+
+def test_ptxas_report_parses_resource_lines(tmp_path):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ptxas_report", os.path.join(ROOT, "tools", "ptxas_report.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    log = tmp_path / "k.log"
+    log.write_text(
+        "nvcc ...\n"
+        "ptxas info    : Compiling entry function '_ZN2dm6kernelEv' for 'sm_100a'\n"
+        "ptxas info    : Function properties for _ZN2dm6kernelEv\n"
+        "    24 bytes stack frame, 44 bytes spill stores, 48 bytes spill loads\n"
+        "ptxas info    : Used 128 registers, used 1 barriers, 16 bytes smem\n"
+        "ptxas info    : Compiling entry function '_ZN2dm5otherEv' for 'sm_100a'\n"
+        "    0 bytes stack frame, 0 bytes spill stores, 0 bytes spill loads\n"
+        "ptxas info    : Used 40 registers\n")
+    rows = mod.parse(str(log))
+    assert [(r["regs"], r["smem"], r["stack"], r["spill_st"], r["spill_ld"], r["barriers"]) for r in rows] == \
+        [(128, 16, 24, 44, 48, 1), (40, 0, 0, 0, 0, 0)]
+    assert mod.demangle(["_ZN2dm6kernelEv"])[0].startswith("dm::kernel")
