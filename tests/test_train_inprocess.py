@@ -124,3 +124,60 @@ def test_evaluator_polls_skips_same_step_and_reports(tmp_path, clean_flags, caps
     FLAGS.parse(["--checkpoint_dir=%s" % (tmp_path / "nothing")])
     assert do_eval(eng, None, ds.validation, FLAGS) == -1
     assert "No checkpoint file found" in capsys.readouterr().out
+
+
+# ---- the GPU path's input pipeline (host code only: page-locked ring, helper threads) with pinning stubbed out ------------------
+def _packer(monkeypatch, dataset, batch, **kw):
+    import torch
+
+    from distributedmnist_b200.train import _BatchPacker
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)      # no CUDA on the CPU tier
+    return _BatchPacker(engine=None, dataset=dataset, batch_size=batch, **kw)
+
+
+def _unpack(buf, batch):
+    import torch
+    n = batch * 784 * 4
+    return buf[:n].view(torch.float32).view(batch, 784).clone().numpy(), buf[n:].view(torch.int64).clone().numpy()
+
+
+@pytest.mark.parametrize("fast_path", [True, False])
+def test_batch_packer_delivers_the_datasets_sequence_in_slot_layout(monkeypatch, fast_path):
+    B = 16
+    twins = [mnist_data.load_mnist("MNIST-data", seed=3, synthetic=True, synthetic_sizes=(80, 16)).train for _ in range(2)]
+    if not fast_path:
+        monkeypatch.delattr(type(twins[0]), "next_batch_indices")
+    p = _packer(monkeypatch, twins[0], B, depth=4, workers=1)
+    try:
+        assert (p._src is not None) == fast_path
+        for _ in range(12):                                  # 12 x 16 = 192 examples: crosses two epoch boundaries of 80
+            img, lbl = _unpack(p.next(), B)
+            ref_img, ref_lbl = twins[1].next_batch(B)
+            np.testing.assert_array_equal(img, np.asarray(ref_img, np.float32).reshape(B, 784))
+            np.testing.assert_array_equal(lbl, np.asarray(ref_lbl).astype(np.int64))
+    finally:
+        p.close()
+    assert not any(t.is_alive() for t in p._threads)
+
+
+def test_batch_packer_with_two_workers_never_hands_out_a_buffer_that_is_being_rewritten(monkeypatch):
+    B = 8
+    ds = mnist_data.load_mnist("MNIST-data", seed=4, synthetic=True, synthetic_sizes=(64, 16)).train
+    key = {np.asarray(ds.images[i], np.float32).reshape(-1).tobytes(): int(ds.labels[i]) for i in range(ds.num_examples)}
+    p = _packer(monkeypatch, ds, B, depth=8, workers=2)
+    try:
+        held = []
+        seen = 0
+        for _ in range(40):
+            buf = p.next()
+            held.append((buf, buf.clone()))
+            held = held[-3:]                                  # the engine may still be copying from the last few buffers
+            for b, snap in held:
+                assert bool((b == snap).all()), "a page-locked buffer changed while the training loop still owned it"
+            img, lbl = _unpack(buf, B)
+            for r in range(B):                                # every row is a real example with its own label
+                assert key[img[r].tobytes()] == int(lbl[r])
+            seen += B
+        assert seen == 320
+    finally:
+        p.close()
