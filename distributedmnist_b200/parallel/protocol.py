@@ -609,12 +609,16 @@ class KofNModel:
     The bitmap slots carry no tag (one ``atomicOr`` per arrival instead of a CAS loop); the committer of step s wipes the slot
     of step s + ring/2.  A replica that stalls for more than ring/2 global steps BETWEEN its commit-word read and its
     ``atomicOr`` therefore leaves a phantom bit -- with the shipped ring of 64 that is a stall of > 32 steps (~4 ms) between
-    two instructions of one warp; the model shows it with ``ring=2`` (``tests/test_protocol.py``).
+    two instructions of one warp; the model shows it with ``ring=2`` (``tests/test_protocol.py``).  ``tagged=True`` models the
+    designed fix (arrival word = (tag, bits), CAS loop, no wipe): no phantom bit under the same schedules.
     """
 
-    def __init__(self, n: int, k: int, steps: int, ring: int = 8, numel: Optional[int] = None, lr: float = 0.5):
+    def __init__(self, n: int, k: int, steps: int, ring: int = 8, numel: Optional[int] = None, lr: float = 0.5,
+                 tagged: bool = False):
         assert 1 <= k <= n and ring >= 2 and ring % 2 == 0
         self.n, self.k, self.steps, self.ring, self.lr = n, k, steps, ring, lr
+        self.tagged = tagged                                                # NEXT_STEPS item 7: (tag, bits) arrival words, CAS loop, no wipe
+        self.bitmap_tag = [0] * ring
         self.numel = numel if numel is not None else n
         self.full = (1 << n) - 1
         self.params = [[(0, 0.0)] * self.numel for _ in range(n)]          # (version = number of updates applied, value)
@@ -654,10 +658,26 @@ class KofNModel:
             yield None
             self.at[r] = ""
             if cw[0] < want:
-                self.bitmap[slot] |= bit                                    # atomicOr_system
-                self.arrived[r] = ep
-                now = self.bitmap[slot] & self.full
-                yield None
+                now = 0
+                if not self.tagged:
+                    self.bitmap[slot] |= bit                                # atomicOr_system
+                    self.arrived[r] = ep
+                    now = self.bitmap[slot] & self.full
+                    yield None
+                else:
+                    while True:                                             # CAS loop on the (tag, bits) arrival word
+                        seen = (self.bitmap_tag[slot], self.bitmap[slot])
+                        yield None
+                        if seen[0] > want:
+                            break                                           # the slot already belongs to a later step: I am stale
+                        new = (want, bit) if seen[0] < want else (want, seen[1] | bit)
+                        if (self.bitmap_tag[slot], self.bitmap[slot]) == seen:
+                            self.bitmap_tag[slot], self.bitmap[slot] = new
+                            self.arrived[r] = ep
+                            now = new[1] & self.full
+                            yield None
+                            break
+                        yield None
                 if popcount(now) >= self.k:
                     old = self.commit[slot]
                     yield None
@@ -682,8 +702,9 @@ class KofNModel:
                                 self.commit_local[q][slot] = (want, now)
                                 if q != r:
                                     yield None
-                            self.bitmap[(slot + ring // 2) % ring] = 0
-                            yield None
+                            if not self.tagged:
+                                self.bitmap[(slot + ring // 2) % ring] = 0
+                                yield None
                 yield (lambda: self.commit_local[r][slot][0] >= want)
                 cw = self.commit_local[r][slot]
             if cw[0] == want:

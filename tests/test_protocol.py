@@ -235,14 +235,14 @@ def test_bucket_v2_model_detects_the_hazards_the_kernels_guard_against():
 
 
 # ---- csrc/fused_sync.cu (K < N): word-level model, sampled schedules with stragglers ---------------------------------------------
-def _kofn_run(seed: int, ring: int, stall_at_commit_word: bool):
+def _kofn_run(seed: int, ring: int, stall_at_commit_word: bool, tagged: bool = False):
     import random
 
     from distributedmnist_b200.parallel.protocol import KofNModel
     rng = random.Random(seed)
     n = rng.choice([2, 3, 4, 8])
     k = rng.randint(1, n - 1) if stall_at_commit_word else rng.randint(1, n)
-    m = KofNModel(n, k, steps=rng.choice([3, 6, 12]), ring=ring)
+    m = KofNModel(n, k, steps=rng.choice([3, 6, 12]), ring=ring, tagged=tagged)
     victim, p = n - 1, rng.choice([0.01, 0.05, 0.3, 1.0])
 
     def choose(runnable):
@@ -275,3 +275,8 @@ def test_kofn_bitmap_ring_tolerates_stalls_below_half_a_lap_and_the_model_sees_l
     with pytest.raises(ProtocolHazard, match="phantom bit"):
         for seed in range(150):
             _kofn_run(seed, ring=2, stall_at_commit_word=True)
+    # the designed fix (NEXT_STEPS item 7): tagged arrival words survive the same stalls even on a two-slot ring
+    dropped = 0
+    for seed in range(300):
+        dropped += sum(_kofn_run(seed, ring=2, stall_at_commit_word=bool(seed % 2), tagged=True).dropped)
+    assert dropped > 100
